@@ -119,13 +119,14 @@ __device__ __forceinline__ void send_item(const adaqp_send_item &it, const adaqp
         hi[r] = warp_max(hi[r]);
         if (__any_sync(ADAQP_FULL_MASK, nan[r])) { lo[r] = __int_as_float(0x7fc00000); hi[r] = lo[r]; }
     }
-    // (3) scale = (2^b - 1) / (max - min) (fp32 IEEE); wire params are bf16(scale), bf16(min)
+    // (3) scale = reciprocal(max - min) * (2^b - 1) as torch evaluates (2**b-1)/(rmax-rmin);
+    //     wire params are bf16(scale), bf16(min)
     float scale[WPT];
     constexpr float levels = (float)((1 << BITS) - 1);
 #pragma unroll
     for (int r = 0; r < WPT; ++r) {
         const float range = __fsub_rn(hi[r], lo[r]);
-        scale[r] = __fdiv_rn(levels, range);
+        scale[r] = __fmul_rn(__frcp_rn(range), levels);  // Tensor.__rtruediv__: reciprocal(range) * levels
         if (lane == r && r < nrows) {
             ch.params[it.param_pos + r] = f32_to_bf16_bits(scale[r]);
             ch.params[ch.S + it.param_pos + r] = f32_to_bf16_bits(lo[r]);

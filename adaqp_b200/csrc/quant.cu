@@ -126,7 +126,7 @@ row_minmax_kernel(const float *__restrict__ data, int64_t N, int64_t F, float le
         if (lane == 0) {
             if (rmin) rmin[n] = lo;
             if (rmax) rmax[n] = hi;
-            if (scale) scale[n] = __fdiv_rn(levels, __fsub_rn(hi, lo));
+            if (scale) scale[n] = __fmul_rn(__frcp_rn(__fsub_rn(hi, lo)), levels);  // torch: reciprocal(range) * levels
         }
     }
 }

@@ -1,0 +1,74 @@
+"""CSR aggregation kernel vs the float64 oracle (ops.py:17-67 semantics).
+
+Tolerance: fp32 accumulation of deg(v) products; bound |err| <= deg * 2^-23 * sum|terms|
+(we assert 2e-5 relative to the row's L1 mass, far above the observed error)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def build(W, n, deg, F, seed=0):
+    from adaqp_b200 import build as b
+    b.build()
+    from adaqp_b200.manager.layout import prepare_all_in_process
+    from adaqp_b200.manager.partition_synth import SynthSpec
+    spec = SynthSpec(name="t", num_nodes=n, num_edges=n * deg, num_parts=W, num_feats=F, num_classes=5,
+                     cross_fraction=0.3 if W > 1 else 0.0, community_size=64, seed=seed)
+    return prepare_all_in_process(spec)
+
+
+def check(got, want, x_abs_rowsum_bound):
+    err = np.abs(got.astype(np.float64) - want)
+    tol = 2e-5 * x_abs_rowsum_bound[:, None] + 1e-6
+    assert np.all(err <= tol), float((err / tol).max())
+
+
+@pytest.mark.parametrize("F", [256, 100, 602, 13, 300, 200, 1])
+@pytest.mark.parametrize("W", [1, 3])
+def test_gcn_and_sage_aggregation(F, W):
+    from adaqp_b200.manager.graph import LocalGraph, spmm
+    dev = torch.device("cuda:0")
+    lays = build(W, 1500, 14, F, seed=F)
+    L = lays[-1]
+    g = LocalGraph(L.indptr, L.indices, L.in_degrees, L.out_degrees, L.n_inner, L.n_halo, dev)
+    rng = np.random.RandomState(F)
+    x = rng.standard_normal((L.n_inner + L.n_halo, F)).astype(np.float32)
+    xl = torch.from_numpy(x[:L.n_inner]).to(dev)
+    xh = torch.from_numpy(x[L.n_inner:]).to(dev) if L.n_halo else None
+    ip, ix = L.indptr, L.indices.astype(np.int64)
+    absx = np.abs(x)
+    mass = O.aggregate(ip, ix, absx).sum(1)
+    # GCN forward / backward
+    got = spmm(g, xl, xh, g.norm["out_-0.5"], g.norm["in_-0.5"]).cpu().numpy()
+    check(got, O.gcn_aggregation(ip, ix, x, L.in_degrees, L.out_degrees, L.n_inner), mass)
+    got = spmm(g, xl, xh, g.norm["in_-0.5"], g.norm["out_-0.5"]).cpu().numpy()
+    check(got, O.gcn_aggregation(ip, ix, x, L.in_degrees, L.out_degrees, L.n_inner, backward=True), mass)
+    # SAGE mean forward / backward
+    got = spmm(g, xl, xh, None, None, mean=True).cpu().numpy()
+    check(got, O.sage_aggregation(ip, ix, x, L.in_degrees, L.out_degrees, L.n_inner), mass)
+    got = spmm(g, xl, xh, g.norm["out_-1"], None).cpu().numpy()
+    check(got, O.sage_aggregation(ip, ix, x, L.in_degrees, L.out_degrees, L.n_inner, backward=True), mass)
+    # central / marginal row ranges == full propagation, row for row (same summation order)
+    full = spmm(g, xl, xh, g.norm["out_-0.5"], g.norm["in_-0.5"])
+    cen = spmm(g, xl, None, g.norm["out_-0.5"], g.norm["in_-0.5"], row_begin=0, row_end=L.n_central)
+    mar = spmm(g, xl, xh, g.norm["out_-0.5"], g.norm["in_-0.5"], row_begin=L.n_central, row_end=L.n_inner)
+    assert torch.equal(torch.cat([cen, mar]), full)
+
+
+def test_strided_and_unaligned_inputs():
+    from adaqp_b200.manager.graph import LocalGraph, spmm
+    dev = torch.device("cuda:0")
+    L = build(2, 800, 10, 64, seed=9)[0]
+    g = LocalGraph(L.indptr, L.indices, L.in_degrees, L.out_degrees, L.n_inner, L.n_halo, dev)
+    rng = np.random.RandomState(0)
+    big = torch.from_numpy(rng.standard_normal((L.n_inner + L.n_halo, 70)).astype(np.float32)).to(dev)
+    for lo, F in [(0, 64), (1, 64), (2, 62), (3, 5)]:
+        xl, xh = big[:L.n_inner, lo:lo + F], big[L.n_inner:, lo:lo + F]
+        got = spmm(g, xl, xh, None, None).cpu().numpy()
+        x = big[:, lo:lo + F].cpu().numpy()
+        want = O.aggregate(L.indptr, L.indices.astype(np.int64), x)
+        check(got, want, O.aggregate(L.indptr, L.indices.astype(np.int64), np.abs(x)).sum(1))
