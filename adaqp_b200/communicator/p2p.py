@@ -435,6 +435,14 @@ class PeerExchange:
         _lib.check(rc, "adaqp_wait_flags")
         return self.halo(key)
 
+    def wait_flags_quant(self, key: str, stream=None):
+        """One-CTA flag wait ahead of the receive kernel, so that a full grid never spins on
+        SMs the overlapped aggregation could use."""
+        plan = self.fp_plans[key]
+        rc = self._lib.adaqp_wait_flags(plan.flags_ptrs.data_ptr(), plan.n_recv, self.seq[key],
+                                        self.status.data_ptr(), self.timeout_ns, _lib.stream_ptr(stream))
+        _lib.check(rc, "adaqp_wait_flags")
+
     def release_fp(self, key: str, stream=None):
         """After the consumer of halo(key) has been enqueued: let the senders overwrite it."""
         plan = self.fp_plans[key]

@@ -1,0 +1,1 @@
+from .graphEngine import DecompGraph, GraphEngine  # noqa: F401

@@ -38,6 +38,8 @@ class Timer(object):
         self._device = device
         self._record = {}
         self._events = {}
+        self._exposed = []
+        self._exposed = []
         self._total_record = []
         self.use_cuda = device is not None and torch.device(device).type == "cuda"
 
@@ -75,6 +77,18 @@ class Timer(object):
         b.record(s)
         self._events[name] = (a, b)
 
+    def record_exposed(self, name: str, compute_done, data_ready):
+        """Exposed communication of one layer pass: how long the default stream had to wait
+        for remote data after its overlappable work finished = max(0, t(data_ready) -
+        t(compute_done)) (the `response.get()` wait of ops.py:177)."""
+        self._exposed.append((name, compute_done, data_ready))
+
+    def exposed_comm_ms(self) -> float:
+        if not self._exposed:
+            return 0.0
+        torch.cuda.synchronize(self._device)
+        return float(sum(max(0.0, a.elapsed_time(b)) for _, a, b in self._exposed))
+
     def epoch_traced_time(self):
         tot = [0.0] * 6
         for name, (start, end) in self._record.items():
@@ -91,3 +105,4 @@ class Timer(object):
             self._total_record.append(self.epoch_traced_time())
         self._record = {}
         self._events = {}
+        self._exposed = []
