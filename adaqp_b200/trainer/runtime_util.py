@@ -62,8 +62,12 @@ def _reduce_group():
     if comm.ctx.device.type != "cuda" or comm.get_world_size() == 1 or not dist.is_nccl_available():
         return None
     if _nccl_group is None:
-        _nccl_group = dist.new_group(backend="nccl")
-    return _nccl_group
+        import os
+        want = os.environ.get("ADAQP_GRAD_REDUCE", "auto").lower()
+        devs = comm.gather_all(str(torch.cuda.get_device_properties(comm.ctx.device).uuid))
+        shared = len(set(devs)) < len(devs)          # NCCL refuses two ranks on one GPU (tests)
+        _nccl_group = False if (want == "gloo" or shared) else dist.new_group(backend="nccl")
+    return _nccl_group or None
 
 
 def sync_model(model: nn.Module):
