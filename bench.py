@@ -67,14 +67,19 @@ class ClockSampler(threading.Thread):
         self.index, self.samples, self.stop_flag = index, [], threading.Event()
 
     def run(self):
+        queries = [self.Q, self.Q.replace("clocks_event_reasons", "clocks_throttle_reasons")]
         while not self.stop_flag.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
+            for q in list(queries):
+                try:
+                    r = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                        "-i", str(self.index)], capture_output=True, text=True, timeout=5)
+                    out = r.stdout.strip()
+                    if r.returncode == 0 and out and out.split(",")[0].strip().isdigit():
+                        self.samples.append([x.strip() for x in out.split(",")])
+                        queries = [q]
+                        break
+                except Exception:
+                    pass
             self.stop_flag.wait(0.2)
 
     def summary(self):
@@ -204,7 +209,6 @@ def run_ours(args, rank, world):
         return traced
 
     ms, traced_all = timed(args.steps, dev_step)
-    sampler.stop_flag.set()
     # ---- end-to-end: host inputs -> device every step, loss read back
     feats_host = eng.feats.cpu().pin_memory()
     labels_host = eng.labels.cpu().pin_memory()
@@ -218,6 +222,7 @@ def run_ours(args, rank, world):
 
     e2e_step()
     ms_e2e, losses = timed(args.steps, e2e_step)
+    sampler.stop_flag.set()
     torch.cuda.synchronize()
     if comm.ctx.comm_buffer.p2p is not None:
         comm.ctx.comm_buffer.p2p.check_status()
