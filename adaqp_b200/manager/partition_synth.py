@@ -12,7 +12,8 @@ communities (label = community id mod classes, features = class centroid + noise
 `homophily` share of the intra-block edges inside communities; truncated power-law node
 weights (Chung-Lu style endpoint sampling, closed-form inverse CDF); every undirected
 edge leaves its block with probability `cross_fraction` towards a uniformly random other
-block; the graph is symmetrised, de-duplicated and given self-loops like
+block, ending on the `boundary_fraction` heaviest nodes of either side (a cut touches only
+part of a partition); the graph is symmetrised, de-duplicated and given self-loops like
 AdaQP/helper/partition.py:58-60.  Every block / block pair has its own seeded stream, so
 rank p builds its partition without materialising the whole graph and both ends of a
 cross edge agree.
@@ -36,6 +37,7 @@ class SynthSpec:
     num_classes: int
     is_multilabel: bool = False
     cross_fraction: float = 0.15
+    boundary_fraction: float = 0.5   # share of a block's nodes that may carry cross-partition edges
     degree_exponent: float = 2.3
     community_size: int = 4096
     homophily: float = 0.6
@@ -61,6 +63,7 @@ def spec_from_config(config: dict, num_parts: int, scale: float = 1.0) -> SynthS
                      num_parts=num_parts, num_feats=int(d["num_feats"]),
                      num_classes=int(d["num_classes"]), is_multilabel=bool(d["is_multilabel"]),
                      cross_fraction=float(s["cross_fraction"]),
+                     boundary_fraction=float(s.get("boundary_fraction", 0.5)),
                      degree_exponent=float(s.get("degree_exponent", 2.3)),
                      community_size=int(s.get("community_size", 4096)),
                      homophily=float(s.get("homophily", 0.6)),
@@ -173,8 +176,12 @@ def _cross_edges(spec: SynthSpec, p: int, q: int, n_p: int, n_q: int) -> Tuple[n
     assert p < q
     _, m = _edge_budget(spec)
     rng = _rng(spec, 31, p, q)
-    a = _perm(spec, p, n_p)[_PowerLaw(n_p, spec.degree_exponent).sample(rng, m)]
-    b = _perm(spec, q, n_q)[_PowerLaw(n_q, spec.degree_exponent).sample(rng, m)]
+    # a METIS cut touches only part of a partition: cross edges end on the block's
+    # `boundary_fraction` highest-weight nodes, the rest stay central (no halo in-neighbour)
+    nb_p = max(1, int(n_p * spec.boundary_fraction))
+    nb_q = max(1, int(n_q * spec.boundary_fraction))
+    a = _perm(spec, p, n_p)[_PowerLaw(nb_p, spec.degree_exponent).sample(rng, m)]
+    b = _perm(spec, q, n_q)[_PowerLaw(nb_q, spec.degree_exponent).sample(rng, m)]
     return a, b
 
 
