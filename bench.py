@@ -120,6 +120,25 @@ def spmm_algorithmic_bytes(eng, dims, use_parallel):
     return total, launches
 
 
+def exchange_stats(ex, eng, traced_all):
+    """Rank 0's boundary traffic per training epoch and the event-timed duration of the
+    exchange kernels (send + wait + receive, side stream): NVLink-side achieved GB/s."""
+    import numpy as np
+    recv_bytes = rows = 0
+    for key, plan in ex.quant_plans.items():
+        for p, (qbytes, n) in plan.wire.items():
+            recv_bytes += qbytes + 4 * n
+            rows += n
+    fp_bytes = sum(4 * ex.dims[k] * ex.num_remote for k in ex.keys if not k.startswith("test"))
+    exch_ms = 1e3 * float(np.mean([t[1] + t[2] for t in traced_all]))      # comm + quant buckets
+    b = recv_bytes if recv_bytes else fp_bytes
+    return {"halo_rows_per_exchange": ex.num_remote, "send_rows_per_exchange": int(eng.total_send_idx.numel()),
+            "bytes_in_per_epoch": int(b), "fp32_equivalent_bytes_per_epoch": int(fp_bytes),
+            "exchange_kernels_ms_per_epoch": exch_ms, "achieved_in_GBps": b / max(exch_ms, 1e-9) / 1e6,
+            "nvlink_peak_GBps_per_direction": 770.0,
+            "note": "exchange kernels are latency/launch bound at this size; they overlap the central aggregation"}
+
+
 def cpu_baseline_port(eng, dims, seconds_budget=20.0):
     """Oracle (C port) of the hot path on the host cores: aggregation over a bounded sample of
     destination rows, extrapolated to one epoch's five aggregations."""
@@ -261,6 +280,7 @@ def run_ours(args, rank, world):
                      "gather_bound": {"note": "no-reuse bound 4*F*nnz: what a random gather must move when the source matrix exceeds L2",
                                       "achieved_GBps": sum(4 * F * int(eng.layout.indptr[-1]) for F in [dims[0], dims[1], dims[2], dims[2], dims[1]]) / (agg_ms * 1e-3) / 1e9}},
         "final_loss": losses[-1],
+        "exchange": exchange_stats(comm.ctx.comm_buffer.p2p, eng, traced_all) if world > 1 else None,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_port(eng, dims)

@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--dataset", type=str, default="ogbn-products")
     ap.add_argument("--json", type=str, default=None)
+    ap.add_argument("--only", type=str, default=None, help="key:bits, e.g. forward1:mixed")
     args = ap.parse_args()
     from adaqp_b200 import build
     build.build()
@@ -56,6 +57,8 @@ def main():
     for key, F in (("forward0", dims[0]), ("forward1", dims[1])):
         xs = [torch.relu(torch.randn(L.n_inner, F, device=dev)) for L in lays]
         for label, pick in (("2bit", [2]), ("4bit", [4]), ("8bit", [8]), ("mixed", [2, 4, 8])):
+            if args.only and args.only != f"{key}:{label}":
+                continue
             assign = [{key: {p: torch.from_numpy(np.array(pick, np.int32)[rng.randint(0, len(pick), hi - lo)])
                              for p, (lo, hi) in L.send_idx.items()}} for L in lays]
             update_quant_in_process(exs, assign)
@@ -86,6 +89,8 @@ def main():
                             "send_frac_hbm": send_bytes / ts / 1e6 / peak, "recv_frac_hbm": recv_bytes / tr / 1e6 / peak})
             print(json.dumps(results[-1]), flush=True)
         # fp32 exchange
+        if args.only and args.only != f"{key}:fp32":
+            continue
         t_fp = []
         for rep in range(args.reps + 3):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
