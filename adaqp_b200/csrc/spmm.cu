@@ -139,69 +139,35 @@ spmm_csr_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ 
 
 
 // ---------------------------------------------------------------------------------------
-// v2: TMA bulk row gather through a per-warp shared-memory ring.
+// v2: asynchronous row gather through a lane-private shared-memory ring (cp.async / LDGSTS).
 //
-// v1 keeps gathered rows in registers, so bytes in flight per SM are bounded by the
-// register file (ncu: 50 % DRAM throughput, 30 % warps active, profiles/r01_*).  Here one
-// elected lane issues a `cp.async.bulk` (UBLKCP) per neighbour row into a ring of kStages
-// row slots per warp; completion is tracked by one mbarrier per slot, the neighbour's norm
-// weight rides along as a 4-byte cp.async, and all lanes consume the slot with LDS.128 +
-// FFMA.  Up to kStages KB-sized rows per warp are in flight with no register cost.  Rows
-// are handed to warps as contiguous nnz-balanced chunks so the ring stays full across row
-// boundaries and hub rows do not serialise a whole CTA.  Each bulk copy carries an L2
-// eviction policy: sources close to the destination id (community / partition-order
-// locality) are kept (evict_last), far ones stream through (evict_first).
+// v1 stages gathered rows in registers: bytes in flight per SM are bounded by the register
+// file and the load -> wait -> consume phases do not overlap (ncu, profiles/r01_*: 50 % DRAM
+// throughput, 30 % warps active).  Here every lane copies its own 16-byte column chunks of
+// each neighbour row with cp.async into a ring of kStages row slots per warp and consumes
+// the oldest slot (LDS.128 + FFMA) while the next kStages-1 rows are still in flight:
+// a continuous software pipeline with no register cost per in-flight row and no cross-lane
+// synchronisation (a lane only ever reads the bytes it copied; completion is tracked by
+// per-thread cp.async groups).  Neighbour ids and their norm weights travel in
+// lane-distributed register windows that are prefetched one and two windows ahead.  Rows
+// are handed to warps as contiguous nnz-balanced chunks, so the pipeline stays full across
+// row boundaries and a hub row costs one warp its own length, not a whole CTA's.
+//
+// Measured alternative (dropped): one `cp.async.bulk` (TMA, UBLKCP) per neighbour row with
+// an mbarrier per slot ran 1.6x-2.2x SLOWER than v1 -- the per-SM bulk-copy engine retires
+// roughly one 0.4-1 KB request per ~60 cycles, far below what a row gather needs
+// (profiles/r01_spmm_variants.md).
 // Requires F % 4 == 0 and 16-byte aligned rows (F = 100, 200, 256, 300 ...); anything else
 // (F = 602) uses v1.
 constexpr int kStages = 8;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t policy) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-        ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
-}
-__device__ __forceinline__ void cp_async_4(uint32_t dst, const void *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ uint64_t make_policy_evict_last() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ uint64_t make_policy_evict_first() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ uint64_t make_policy_evict_normal() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // first row r in [lo, hi] with indptr[r] >= target
 __device__ __forceinline__ int64_t row_lower_bound(const int64_t *__restrict__ indptr, int64_t lo, int64_t hi, int64_t target) {
@@ -214,31 +180,19 @@ __device__ __forceinline__ int64_t row_lower_bound(const int64_t *__restrict__ i
 
 template <int CHUNKS>
 __global__ void __launch_bounds__(kThreads)
-spmm_csr_tma_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices,
-                    const float *__restrict__ x0, int64_t ld0, int64_t n_split,
-                    const float *__restrict__ x1, int64_t ld1,
-                    const float *__restrict__ pre, const float *__restrict__ post,
-                    int mean, int add_self, int64_t row_begin, int64_t row_end, int F,
-                    float *__restrict__ out, int64_t ldo, int64_t chunk_nnz,
-                    int64_t near_window, int use_hints) {
+spmm_csr_ring_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                     const float *__restrict__ x0, int64_t ld0, int64_t n_split,
+                     const float *__restrict__ x1, int64_t ld1,
+                     const float *__restrict__ pre, const float *__restrict__ post,
+                     int mean, int add_self, int64_t row_begin, int64_t row_end, int F,
+                     float *__restrict__ out, int64_t ldo, int64_t chunk_nnz) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
-    const int row_bytes = F * 4;
-    const int slot_bytes = (row_bytes + 127) & ~127;
-    uint8_t *ring = smem_raw + (size_t)wib * kStages * slot_bytes;
-    float *wslot = reinterpret_cast<float *>(smem_raw + (size_t)kWarps * kStages * slot_bytes) + wib * kStages;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kWarps * kStages * slot_bytes + kWarps * kStages * 4) + wib * kStages;
-    const uint32_t ring_u = smem_u32(ring), wslot_u = smem_u32(wslot), bars_u = smem_u32(bars);
-    if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < kStages; ++s) mbar_init(bars_u + 8 * s, 2);   // expect_tx arrive + weight arrive
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    __syncwarp();
-    const uint64_t pol_near = make_policy_evict_last();
-    const uint64_t pol_far = make_policy_evict_first();
-    const uint64_t pol_norm = make_policy_evict_normal();
+    // ring[warp][stage][chunk][lane] of 16 bytes: a lane's chunk is contiguous with its
+    // neighbours' (conflict-free LDS.128 / LDGSTS.128)
+    const uint32_t ring_u = smem_u32(smem_raw) + (uint32_t)wib * kStages * CHUNKS * 512u + (uint32_t)lane * 16u;
+    const float4 *ring = reinterpret_cast<const float4 *>(smem_raw) + (size_t)wib * kStages * CHUNKS * 32 + lane;
 
     bool colok[CHUNKS];
 #pragma unroll
@@ -247,30 +201,58 @@ spmm_csr_tma_kernel(const int64_t *__restrict__ indptr, const int32_t *__restric
     const int64_t nnz_end_all = __ldg(indptr + row_end);
     int64_t n_chunks = (nnz_end_all - nnz_base + chunk_nnz - 1) / chunk_nnz;
     if (n_chunks < 1) n_chunks = 1;   // rows without edges still produce output
-    uint32_t issued = 0, consumed = 0;   // ring counters (monotone across chunks)
 
     const int64_t warp = (int64_t)blockIdx.x * kWarps + wib;
     const int64_t nwarps = (int64_t)gridDim.x * kWarps;
     for (int64_t chunk = warp; chunk < n_chunks; chunk += nwarps) {
         // rows whose first nnz falls into this chunk's nnz window
         const int64_t lo_nnz = nnz_base + chunk * chunk_nnz;
-        int64_t hi_nnz = lo_nnz + chunk_nnz;
         const bool last = (chunk == n_chunks - 1);
         const int64_t r0 = (chunk == 0) ? row_begin : row_lower_bound(indptr, row_begin, row_end, lo_nnz);
-        const int64_t r1 = last ? row_end : row_lower_bound(indptr, row_begin, row_end, hi_nnz);
+        const int64_t r1 = last ? row_end : row_lower_bound(indptr, row_begin, row_end, lo_nnz + chunk_nnz);
         if (r0 >= r1) continue;
-        int64_t pc = __ldg(indptr + r0);
+        int64_t pc = __ldg(indptr + r0);                       // consume cursor
         const int64_t pend = last ? nnz_end_all : __ldg(indptr + r1);
-        int64_t pi = pc;
-        // index window of the issue side (32 ids per lane-distributed window) + prefetched next window
-        int64_t wb = pi;
+        int64_t pi = pc;                                       // issue cursor
+        // lane-distributed windows of 32 neighbour ids / weights: [cur | nxt | nx2 (ids only)]
+        int64_t wb = pc;
         int idx_cur = (wb + lane < pend) ? __ldg(indices + wb + lane) : 0;
-        int idx_next = (wb + 32 + lane < pend) ? __ldg(indices + wb + 32 + lane) : 0;
+        int idx_nxt = (wb + 32 + lane < pend) ? __ldg(indices + wb + 32 + lane) : 0;
+        int idx_nx2 = (wb + 64 + lane < pend) ? __ldg(indices + wb + 64 + lane) : 0;
+        float w_cur = (pre && wb + lane < pend) ? __ldg(pre + idx_cur) : 1.f;
+        float w_nxt = (pre && wb + 32 + lane < pend) ? __ldg(pre + idx_nxt) : 1.f;
+        float w_prev = 1.f;   // the consume side lags the issue side by < kStages <= 32 ids
         int64_t row = r0;
         int64_t rend = __ldg(indptr + row + 1);
         float acc[CHUNKS][4];
 #pragma unroll
         for (int c = 0; c < CHUNKS; ++c) { acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f; }
+        uint32_t si = 0, sc = 0;                               // ring positions
+
+        auto issue_one = [&]() {
+            if (pi < pend) {
+                if (pi >= wb + 32) {                           // slide the issue windows
+                    wb += 32;
+                    idx_cur = idx_nxt; idx_nxt = idx_nx2;
+                    idx_nx2 = (wb + 64 + lane < pend) ? __ldg(indices + wb + 64 + lane) : 0;
+                    w_prev = w_cur;
+                    w_cur = w_nxt;
+                    w_nxt = (pre && wb + 32 + lane < pend) ? __ldg(pre + idx_nxt) : 1.f;
+                }
+                const int u = __shfl_sync(ADAQP_FULL_MASK, idx_cur, (int)(pi - wb));
+                const float *src = (u < n_split) ? (x0 + (int64_t)u * ld0) : (x1 + ((int64_t)u - n_split) * ld1);
+                const uint32_t dst = ring_u + (si % kStages) * (CHUNKS * 512u);
+#pragma unroll
+                for (int c = 0; c < CHUNKS; ++c)
+                    if (colok[c]) cp_async_16(dst + c * 512u, src + (c * 32 + lane) * 4);
+                ++pi;
+                ++si;
+            }
+            cp_async_commit();                                 // empty groups keep the queue depth constant
+        };
+
+#pragma unroll 1
+        for (int k = 0; k < kStages - 1; ++k) issue_one();     // prologue: fill the pipeline
 
         while (true) {
             // ---- finish every row that is complete (also rows without in-edges)
@@ -305,52 +287,22 @@ spmm_csr_tma_kernel(const int64_t *__restrict__ indptr, const int32_t *__restric
                 if (row < r1) rend = __ldg(indptr + row + 1);
             }
             if (pc >= pend) break;
-            // ---- top up the ring: keep kStages row gathers in flight
-            while (pi < pend && (uint32_t)(issued - consumed) < (uint32_t)kStages) {
-                if (pi >= wb + 32) {            // slide the window; the next one was prefetched 32 ids ago
-                    wb += 32;
-                    idx_cur = idx_next;
-                    idx_next = (wb + 32 + lane < pend) ? __ldg(indices + wb + 32 + lane) : 0;
-                }
-                const int u = __shfl_sync(ADAQP_FULL_MASK, idx_cur, (int)(pi - wb));
-                if (lane == 0) {
-                    const uint32_t s = issued % kStages;
-                    const uint32_t bar = bars_u + 8 * s;
-                    const float *src = (u < n_split) ? (x0 + (int64_t)u * ld0) : (x1 + ((int64_t)u - n_split) * ld1);
-                    uint64_t pol = pol_norm;
-                    if (use_hints) {
-                        const int64_t dist = (int64_t)u - row;
-                        pol = (u >= n_split) ? pol_norm : ((dist < near_window && dist > -near_window) ? pol_near : pol_far);
-                    }
-                    if (pre) {
-                        cp_async_4(wslot_u + 4 * s, pre + u);
-                        cp_async_mbar_arrive_noinc(bar);
-                    } else {
-                        mbar_arrive(bar);
-                    }
-                    mbar_arrive_expect_tx(bar, (uint32_t)row_bytes);
-                    bulk_g2s(ring_u + s * slot_bytes, src, (uint32_t)row_bytes, bar, pol);
-                }
-                ++issued;
-                ++pi;
-            }
-            // ---- consume the oldest slot
-            {
-                const uint32_t s = consumed % kStages;
-                mbar_wait(bars_u + 8 * s, (consumed / kStages) & 1u);
-                const float w = pre ? wslot[s] : 1.f;
-                const uint8_t *slot = ring + s * slot_bytes;
+            issue_one();                                       // one more row in flight ...
+            cp_async_wait<kStages - 1>();                      // ... and the oldest has landed (for this lane)
+            const float wa = __shfl_sync(ADAQP_FULL_MASK, w_cur, (int)((pc - wb) & 31));
+            const float wp = __shfl_sync(ADAQP_FULL_MASK, w_prev, (int)((pc - wb + 32) & 31));
+            const float w = (pc >= wb) ? wa : wp;
+            const float4 *slot = ring + (size_t)(sc % kStages) * (CHUNKS * 32);
 #pragma unroll
-                for (int c = 0; c < CHUNKS; ++c) if (colok[c]) {
-                    const float4 t = *reinterpret_cast<const float4 *>(slot + (c * 32 + lane) * 16);
-                    acc[c][0] = __fmaf_rn(w, t.x, acc[c][0]); acc[c][1] = __fmaf_rn(w, t.y, acc[c][1]);
-                    acc[c][2] = __fmaf_rn(w, t.z, acc[c][2]); acc[c][3] = __fmaf_rn(w, t.w, acc[c][3]);
-                }
-                ++consumed;
-                ++pc;
-                __syncwarp();   // every lane is done with the slot before lane 0 refills it
+            for (int c = 0; c < CHUNKS; ++c) if (colok[c]) {
+                const float4 t = slot[c * 32];
+                acc[c][0] = __fmaf_rn(w, t.x, acc[c][0]); acc[c][1] = __fmaf_rn(w, t.y, acc[c][1]);
+                acc[c][2] = __fmaf_rn(w, t.z, acc[c][2]); acc[c][3] = __fmaf_rn(w, t.w, acc[c][3]);
             }
+            ++sc;
+            ++pc;
         }
+        cp_async_wait<0>();
     }
 }
 
@@ -383,40 +335,30 @@ int adaqp_spmm_csr_f32(const int64_t *indptr, const int32_t *indices, const floa
     const int64_t cap = (int64_t)sms * 8;
     if (grid > cap) grid = cap;
     cudaStream_t s = (cudaStream_t)stream;
-    // v2 (TMA ring) needs 16-byte rows: F % 4 == 0, strides % 4 == 0, 16-byte aligned bases
-    static int impl = -1, hints = -1;
+    // v2 (cp.async ring) needs 16-byte rows: F % 4 == 0, strides % 4 == 0, 16-byte aligned bases
+    static int impl = -1;
     if (impl < 0) { const char *e = getenv("ADAQP_SPMM"); impl = (e && e[0] == '1') ? 1 : ((e && e[0] == '2') ? 2 : 0); }
-    if (hints < 0) { const char *e = getenv("ADAQP_SPMM_HINTS"); hints = (e && e[0] == '0') ? 0 : 1; }
     if (impl != 1 && vec == 4 && nchunks <= 8) {
-        const int slot_bytes = (F * 4 + 127) & ~127;
-        const size_t smem = (size_t)kWarps * kStages * slot_bytes + kWarps * kStages * 4 + kWarps * kStages * 8;
-        int ctas_per_sm = (int)((200 * 1024) / (smem + 1024));
-        if (ctas_per_sm > 4) ctas_per_sm = 4;
-        if (ctas_per_sm < 1) ctas_per_sm = 1;
-        int64_t g2 = (int64_t)sms * ctas_per_sm;
-        const int64_t max_ctas = (rows + kWarps - 1) / kWarps;
-        if (g2 > max_ctas) g2 = max_ctas;
-        const int64_t chunk_nnz = 2048;       // nnz-balanced work units, many per warp
-        const int64_t near_window = 16384;    // |src - dst| below this: keep the row in L2
-#define CALL_V2(C)                                                                                   \
-    do {                                                                                             \
-        static bool attr_set_##C = false;                                                            \
-        if (!attr_set_##C) {                                                                         \
-            cudaFuncSetAttribute(spmm_csr_tma_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
-            attr_set_##C = true;                                                                     \
-        }                                                                                            \
-        spmm_csr_tma_kernel<C><<<(unsigned)g2, kThreads, smem, s>>>(indptr, indices, x0, ld0, n_split, x1, ld1, \
-                                                                 pre, post, mean, add_self, row_begin, row_end, \
-                                                                 F, out, ldo, chunk_nnz, near_window, hints);   \
-    } while (0)
-        if (nchunks <= 1) CALL_V2(1);
-        else if (nchunks <= 2) CALL_V2(2);
-        else if (nchunks <= 3) CALL_V2(3);
-        else if (nchunks <= 4) CALL_V2(4);
-        else if (nchunks <= 6) CALL_V2(6);
-        else CALL_V2(8);
-#undef CALL_V2
-        return adaqp_check_launch("spmm_csr_tma_kernel");
+        auto launch = [&](auto kernel, int C) {
+            const size_t smem = (size_t)kWarps * kStages * C * 512;
+            int ctas_per_sm = (int)((200 * 1024) / (smem + 1024));
+            if (ctas_per_sm > 4) ctas_per_sm = 4;
+            if (ctas_per_sm < 1) ctas_per_sm = 1;
+            int64_t g2 = (int64_t)sms * ctas_per_sm;
+            const int64_t max_ctas = (rows + kWarps - 1) / kWarps;
+            if (g2 > max_ctas) g2 = max_ctas;
+            const int64_t chunk_nnz = 2048;   // nnz-balanced work units, many per warp
+            cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            kernel<<<(unsigned)g2, kThreads, smem, s>>>(indptr, indices, x0, ld0, n_split, x1, ld1, pre, post, mean,
+                                                        add_self, row_begin, row_end, F, out, ldo, chunk_nnz);
+        };
+        if (nchunks <= 1) launch(spmm_csr_ring_kernel<1>, 1);
+        else if (nchunks <= 2) launch(spmm_csr_ring_kernel<2>, 2);
+        else if (nchunks <= 3) launch(spmm_csr_ring_kernel<3>, 3);
+        else if (nchunks <= 4) launch(spmm_csr_ring_kernel<4>, 4);
+        else if (nchunks <= 6) launch(spmm_csr_ring_kernel<6>, 6);
+        else launch(spmm_csr_ring_kernel<8>, 8);
+        return adaqp_check_launch("spmm_csr_ring_kernel");
     }
 #define CALL_SPMM(V, C)                                                                           \
     spmm_csr_kernel<V, C><<<(unsigned)grid, kThreads, 0, s>>>(indptr, indices, x0, ld0, n_split, x1, \
