@@ -337,8 +337,8 @@ int adaqp_spmm_csr_f32(const int64_t *indptr, const int32_t *indices, const floa
     cudaStream_t s = (cudaStream_t)stream;
     // v2 (cp.async ring) needs 16-byte rows: F % 4 == 0, strides % 4 == 0, 16-byte aligned bases
     static int impl = -1;
-    if (impl < 0) { const char *e = getenv("ADAQP_SPMM"); impl = (e && e[0] == '1') ? 1 : ((e && e[0] == '2') ? 2 : 0); }
-    if (impl != 1 && vec == 4 && nchunks <= 8) {
+    if (impl < 0) { const char *e = getenv("ADAQP_SPMM"); impl = (e && e[0] == '2') ? 2 : 1; }   // default v1
+    if (impl == 2 && vec == 4 && nchunks <= 8) {
         auto launch = [&](auto kernel, int C) {
             const size_t smem = (size_t)kWarps * kStages * C * 512;
             int ctas_per_sm = (int)((200 * 1024) / (smem + 1024));
