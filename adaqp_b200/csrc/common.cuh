@@ -57,6 +57,46 @@ __device__ __forceinline__ float uniform_from_u32(uint32_t x) {
     return __fmaf_rn(__uint2float_rn(x), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
 }
 
+// Round keys precomputed on the host and passed as a __grid_constant__ kernel parameter:
+// the 20 key-schedule adds per block disappear and LOP3 reads the keys straight from the
+// constant bank.
+struct PhiloxKeys {
+    uint32_t kx[10];
+    uint32_t ky[10];
+};
+
+static inline PhiloxKeys make_philox_keys(uint64_t seed) {
+    PhiloxKeys K;
+    uint32_t x = (uint32_t)seed, y = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        K.kx[r] = x;
+        K.ky[r] = y;
+        x += PHILOX_W0;
+        y += PHILOX_W1;
+    }
+    return K;
+}
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, const PhiloxKeys &K) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)PHILOX_M0 * c.x;
+        const uint64_t p1 = (uint64_t)PHILOX_M1 * c.z;
+        c = make_uint4((uint32_t)(p1 >> 32) ^ c.y ^ K.kx[r], (uint32_t)p1, (uint32_t)(p0 >> 32) ^ c.w ^ K.ky[r], (uint32_t)p0);
+    }
+    return c;
+}
+
+// Fast-path noise for torch-style offsets (offset % 4 == 0) and WPT <= 4: one block per byte.
+template <int WPT>
+__device__ __forceinline__ void byte_noise_fast(const PhiloxKeys &K, uint32_t blk_lo, uint32_t blk_hi,
+                                                uint32_t k_lo, uint32_t k_hi, float (&u)[WPT]) {
+    const uint4 a = philox4x32_10(make_uint4(blk_lo, blk_hi, k_lo, k_hi), K);
+    u[0] = uniform_from_u32(a.x);
+    if (WPT > 1) u[1 % WPT] = uniform_from_u32(a.y);
+    if (WPT > 2) { u[2 % WPT] = uniform_from_u32(a.z); u[3 % WPT] = uniform_from_u32(a.w); }
+}
+
 // The uniforms the reference draws for packed byte `k` of a pack call whose generator
 // inputs are (seed, offset): curand_init(seed, subsequence = k, offset) followed by
 // WPT = 8/bits curand_uniform draws.  Draw i is word (offset%4 + i)%4 of the Philox

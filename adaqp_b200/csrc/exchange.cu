@@ -72,11 +72,13 @@ __device__ __forceinline__ void warp_copy_out(uint8_t *dst, const uint8_t *src, 
 }
 
 // ------------------------------------------------------------------ sender
-template <int BITS, int VEC, int CHUNKS>
+// FULL: every row of the byte-row exists and F == 32 * VEC * CHUNKS, so no row / column
+// predicates are needed (the common case: F = 256, all but the last byte-row of a segment).
+template <int BITS, int VEC, int CHUNKS, bool FULL>
 __device__ __forceinline__ void send_item(const adaqp_send_item &it, const adaqp_send_chan &ch,
                                           const float *__restrict__ x, int64_t ld, int F,
                                           float *__restrict__ trace, float trace_coef,
-                                          uint64_t seed, uint64_t base_offset,
+                                          const PhiloxKeys &keys, uint64_t seed, uint64_t base_offset,
                                           uint8_t *stage, int lane) {
     constexpr int WPT = 8 / BITS;
     float v[WPT][CHUNKS][VEC];
@@ -91,7 +93,7 @@ __device__ __forceinline__ void send_item(const adaqp_send_item &it, const adaqp
 #pragma unroll
         for (int c = 0; c < CHUNKS; ++c) {
             const int col = (c * 32 + lane) * VEC;
-            if (r < nrows && col < F) {
+            if (FULL || (r < nrows && col < F)) {
                 RowVec<VEC>::load(x + (int64_t)row * ld + col, v[r][c]);
             } else {
 #pragma unroll
@@ -105,7 +107,7 @@ __device__ __forceinline__ void send_item(const adaqp_send_item &it, const adaqp
 #pragma unroll
         for (int c = 0; c < CHUNKS; ++c) {
             const int col = (c * 32 + lane) * VEC;
-            if (col < F) {
+            if (FULL || col < F) {
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) {
                     const float t = v[r][c][e];
@@ -127,7 +129,7 @@ __device__ __forceinline__ void send_item(const adaqp_send_item &it, const adaqp
     for (int r = 0; r < WPT; ++r) {
         const float range = __fsub_rn(hi[r], lo[r]);
         scale[r] = __fmul_rn(__frcp_rn(range), levels);  // Tensor.__rtruediv__: reciprocal(range) * levels
-        if (lane == r && r < nrows) {
+        if (lane == r && (FULL || r < nrows)) {
             ch.params[it.param_pos + r] = f32_to_bf16_bits(scale[r]);
             ch.params[ch.S + it.param_pos + r] = f32_to_bf16_bits(lo[r]);
             if (trace) {  // trace_input: (dim / 6) * (rmax - rmin) ** 2, op_util.py:95-97
@@ -141,18 +143,22 @@ __device__ __forceinline__ void send_item(const adaqp_send_item &it, const adaqp
     const int phase16 = (int)(reinterpret_cast<uintptr_t>(dst) & 15u);
     const uint64_t offset = base_offset + it.rel_offset;
     const uint64_t kbase = (uint64_t)it.group * (uint64_t)F;
+    const bool fast_rng = (offset & 3u) == 0;       // always true for torch generators
+    const uint64_t blk = offset >> 2;
 #pragma unroll
     for (int c = 0; c < CHUNKS; ++c) {
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
             const int col = (c * 32 + lane) * VEC + e;
-            if (col < F) {
+            if (FULL || col < F) {
                 float u[WPT];
-                byte_noise<WPT>(seed, kbase + (uint64_t)col, offset, u);
+                const uint64_t k = kbase + (uint64_t)col;
+                if (fast_rng) byte_noise_fast<WPT>(keys, (uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)k, (uint32_t)(k >> 32), u);
+                else byte_noise<WPT>(seed, k, offset, u);
                 uint32_t byte = 0;
 #pragma unroll
                 for (int r = 0; r < WPT; ++r) {
-                    if (r < nrows) {
+                    if (FULL || r < nrows) {
                         const int q = quantize_one(v[r][c][e], lo[r], scale[r], u[r]);
                         byte |= ((uint32_t)q << (r * BITS));
                     }
@@ -168,12 +174,12 @@ __device__ __forceinline__ void send_item(const adaqp_send_item &it, const adaqp
 }
 
 template <int VEC, int CHUNKS>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, (VEC * CHUNKS <= 8) ? 3 : 1)
 send_quant_kernel(const float *__restrict__ x, int64_t ld, int F,
                   const adaqp_send_item *__restrict__ items, int64_t n_items,
                   const adaqp_send_chan *__restrict__ chans, int n_chans,
-                  float *__restrict__ trace, uint64_t seed, uint64_t base_offset, uint32_t seq,
-                  uint32_t *work, uint32_t *status, uint64_t timeout_ns) {
+                  float *__restrict__ trace, const __grid_constant__ PhiloxKeys keys, uint64_t seed,
+                  uint64_t base_offset, uint32_t seq, uint32_t *work, uint32_t *status, uint64_t timeout_ns) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
@@ -185,12 +191,10 @@ send_quant_kernel(const float *__restrict__ x, int64_t ld, int F,
     int acked = -1;  // channel whose slab is known to be free for this seq
     for (int64_t i = warp; i < n_items; i += nwarps) {
         adaqp_send_item it;
-        {   // 64-byte item: 16 lanes x 4 bytes, broadcast through shuffles
-            const uint32_t *p = reinterpret_cast<const uint32_t *>(items + i);
-            const uint32_t w = __ldg(p + (lane & 15));
-            uint32_t *q = reinterpret_cast<uint32_t *>(&it);
-#pragma unroll
-            for (int k = 0; k < 16; ++k) q[k] = __shfl_sync(ADAQP_FULL_MASK, w, k);
+        {   // 64-byte item through four uniform 16-byte loads (broadcast by L1)
+            const uint4 *p = reinterpret_cast<const uint4 *>(items + i);
+            uint4 *q = reinterpret_cast<uint4 *>(&it);
+            q[0] = __ldg(p); q[1] = __ldg(p + 1); q[2] = __ldg(p + 2); q[3] = __ldg(p + 3);
         }
         const adaqp_send_chan ch = chans[it.chan];
         if (it.chan != acked) {
@@ -201,11 +205,18 @@ send_quant_kernel(const float *__restrict__ x, int64_t ld, int F,
             if (!ok && lane == 0) report(status, ADAQP_ST_ACK_TIMEOUT, (uint32_t)it.chan);
             acked = it.chan;
         }
+        const bool full = (F == 32 * VEC * CHUNKS) && (it.nrows * it.bits == 8);
+#define ADAQP_SEND(B)                                                                                          \
+    do {                                                                                                       \
+        if (full) send_item<B, VEC, CHUNKS, true>(it, ch, x, ld, F, trace, trace_coef, keys, seed, base_offset, stage, lane);  \
+        else send_item<B, VEC, CHUNKS, false>(it, ch, x, ld, F, trace, trace_coef, keys, seed, base_offset, stage, lane);      \
+    } while (0)
         switch (it.bits) {
-            case 2: send_item<2, VEC, CHUNKS>(it, ch, x, ld, F, trace, trace_coef, seed, base_offset, stage, lane); break;
-            case 4: send_item<4, VEC, CHUNKS>(it, ch, x, ld, F, trace, trace_coef, seed, base_offset, stage, lane); break;
-            default: send_item<8, VEC, CHUNKS>(it, ch, x, ld, F, trace, trace_coef, seed, base_offset, stage, lane); break;
+            case 2: ADAQP_SEND(2); break;
+            case 4: ADAQP_SEND(4); break;
+            default: ADAQP_SEND(8); break;
         }
+#undef ADAQP_SEND
     }
     // publish: every thread's peer stores are fenced, the last CTA raises the flags
     __threadfence_system();
@@ -291,11 +302,9 @@ recv_quant_kernel(float *__restrict__ halo, int64_t ld, int F,
     for (int64_t i = warp; i < n_items; i += nwarps) {
         adaqp_recv_item it;
         {
-            const uint32_t *p = reinterpret_cast<const uint32_t *>(items + i);
-            const uint32_t w = __ldg(p + (lane & 7));
-            uint32_t *q = reinterpret_cast<uint32_t *>(&it);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) q[k] = __shfl_sync(ADAQP_FULL_MASK, w, k);
+            const uint4 *p = reinterpret_cast<const uint4 *>(items + i);
+            uint4 *q = reinterpret_cast<uint4 *>(&it);
+            q[0] = __ldg(p); q[1] = __ldg(p + 1);
         }
         const adaqp_recv_chan ch = chans[it.chan];
         if (it.chan != ready) {
@@ -455,10 +464,11 @@ int adaqp_send_quant(const float *x, int64_t ld, int32_t F, const adaqp_send_ite
     const int stage_stride = ((F + 16 + 15) >> 4) << 4;
     const size_t smem = (size_t)kWarps * stage_stride;
     const int grid = grid_for(n_items, 4);
+    const PhiloxKeys keys = make_philox_keys(seed);
     cudaStream_t s = (cudaStream_t)stream;
 #define CALL_SEND(V, C)                                                                          \
     send_quant_kernel<V, C><<<grid, kThreads, smem, s>>>(x, ld, F, items, n_items, chans, n_chans, \
-                                                         trace, seed, base_offset, seq, work,     \
+                                                         trace, keys, seed, base_offset, seq, work, \
                                                          status, timeout_ns)
     if (vec == 4) {
         if (nchunks <= 1) CALL_SEND(4, 1);

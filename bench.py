@@ -215,10 +215,10 @@ def run_ours(args, rank, world):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), extras
 
+    sampler = ClockSampler(dev.index or 0)      # samples under load from the warm-up on
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step(eng.feats, eng.labels)
-    sampler = ClockSampler(dev.index or 0)
-    sampler.start()
     exposed, agg_s = [], []
 
     def dev_step():
