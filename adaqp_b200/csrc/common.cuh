@@ -150,6 +150,15 @@ __device__ __forceinline__ int quantize_one(float x, float mn, float scale, floa
     return __float2int_rn(f);
 }
 
+// val / scale for a small non-negative integer val, bit-identical to the reference's IEEE
+// division.  A zero numerator (every row minimum quantises to 0; relu'd rows are mostly 0)
+// sends nvcc's division sequence (FCHK) to its slow-path subroutine, so the quotient for 0 is
+// computed once per row (q_zero = __fdiv_rn(0.f, scale): +0, or NaN for scale 0 / NaN) and
+// selected here; non-zero numerators with normal scales stay on the fast path.
+__device__ __forceinline__ float dequant_div(uint32_t ival, float scale, float q_zero) {
+    return ival == 0u ? q_zero : __fdiv_rn((float)ival, scale);
+}
+
 // fp32 -> bf16 bits with c10::BFloat16 semantics (RNE, NaN -> 0x7FC0).
 __device__ __forceinline__ uint16_t f32_to_bf16_bits(float f) {
     if (f != f) return (uint16_t)0x7FC0;

@@ -239,7 +239,7 @@ __device__ __forceinline__ void recv_item(const adaqp_recv_item &it, const adaqp
     constexpr uint32_t MASK = (1u << BITS) - 1u;
     const uint8_t *src = ch.qdata + it.src_off;
     const int nrows = it.nrows;
-    float scale[WPT], mn[WPT];
+    float scale[WPT], mn[WPT], qz[WPT];
 #pragma unroll
     for (int r = 0; r < WPT; ++r) {
         if (r < nrows) {
@@ -248,6 +248,7 @@ __device__ __forceinline__ void recv_item(const adaqp_recv_item &it, const adaqp
         } else {
             scale[r] = 1.f; mn[r] = 0.f;
         }
+        qz[r] = __fdiv_rn(0.f, scale[r]);
     }
     uint32_t bytes[CHUNKS][VEC];
     if (VEC == 4 && (reinterpret_cast<uintptr_t>(src) & 3u) == 0) {  // warp-uniform
@@ -279,8 +280,8 @@ __device__ __forceinline__ void recv_item(const adaqp_recv_item &it, const adaqp
                     float o[VEC];
 #pragma unroll
                     for (int e = 0; e < VEC; ++e) {
-                        const float val = (float)((bytes[c][e] >> (r * BITS)) & MASK);
-                        o[e] = __fadd_rn(__fdiv_rn(val, scale[r]), mn[r]);  // IEEE div then add, as unpack
+                        const uint32_t ival = (bytes[c][e] >> (r * BITS)) & MASK;
+                        o[e] = __fadd_rn(dequant_div(ival, scale[r], qz[r]), mn[r]);  // IEEE div then add, as unpack
                     }
                     RowVec<VEC>::store(orow + col, o);
                 }

@@ -75,11 +75,12 @@ unpack_flat_kernel(const uint8_t *__restrict__ packed, const float *__restrict__
             const int64_t n = no * WPT + ni;
             if (n < N) {
                 const float s = __ldg(scale + n), m = __ldg(mn + n);
+                const float qz = __fdiv_rn(0.f, s);
                 float4 v;
-                v.x = __fadd_rn(__fdiv_rn((float)((word >> (ni * BITS)) & MASK), s), m);
-                v.y = __fadd_rn(__fdiv_rn((float)((word >> (8 + ni * BITS)) & MASK), s), m);
-                v.z = __fadd_rn(__fdiv_rn((float)((word >> (16 + ni * BITS)) & MASK), s), m);
-                v.w = __fadd_rn(__fdiv_rn((float)((word >> (24 + ni * BITS)) & MASK), s), m);
+                v.x = __fadd_rn(dequant_div((word >> (ni * BITS)) & MASK, s, qz), m);
+                v.y = __fadd_rn(dequant_div((word >> (8 + ni * BITS)) & MASK, s, qz), m);
+                v.z = __fadd_rn(dequant_div((word >> (16 + ni * BITS)) & MASK, s, qz), m);
+                v.w = __fadd_rn(dequant_div((word >> (24 + ni * BITS)) & MASK, s, qz), m);
                 *reinterpret_cast<float4 *>(out + n * F + d) = v;
             }
         }
