@@ -87,6 +87,22 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, const PhiloxKeys &K) {
     return c;
 }
 
+// N independent Philox blocks advanced round by round: the 10-round dependency chain of one
+// block (IMAD.WIDE -> LOP3 -> ...) leaves the issue slots idle, N interleaved chains fill them.
+template <int N>
+__device__ __forceinline__ void philox4x32_10_xN(uint4 (&c)[N], const PhiloxKeys &K) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            const uint64_t p0 = (uint64_t)PHILOX_M0 * c[j].x;
+            const uint64_t p1 = (uint64_t)PHILOX_M1 * c[j].z;
+            c[j] = make_uint4((uint32_t)(p1 >> 32) ^ c[j].y ^ K.kx[r], (uint32_t)p1,
+                              (uint32_t)(p0 >> 32) ^ c[j].w ^ K.ky[r], (uint32_t)p0);
+        }
+    }
+}
+
 // Fast-path noise for torch-style offsets (offset % 4 == 0) and WPT <= 4: one block per byte.
 template <int WPT>
 __device__ __forceinline__ void byte_noise_fast(const PhiloxKeys &K, uint32_t blk_lo, uint32_t blk_hi,

@@ -78,7 +78,7 @@ template <int BITS, int VEC, int CHUNKS, bool FULL>
 __device__ __forceinline__ void send_item(const adaqp_send_item &it, const adaqp_send_chan &ch,
                                           const float *__restrict__ x, int64_t ld, int F,
                                           float *__restrict__ trace, float trace_coef,
-                                          const PhiloxKeys &keys, uint64_t seed, uint64_t base_offset,
+                                          const PhiloxKeys &keys, uint64_t base_offset,
                                           uint8_t *stage, int lane) {
     constexpr int WPT = 8 / BITS;
     float v[WPT][CHUNKS][VEC];
@@ -143,27 +143,32 @@ __device__ __forceinline__ void send_item(const adaqp_send_item &it, const adaqp
     const int phase16 = (int)(reinterpret_cast<uintptr_t>(dst) & 15u);
     const uint64_t offset = base_offset + it.rel_offset;
     const uint64_t kbase = (uint64_t)it.group * (uint64_t)F;
-    const bool fast_rng = (offset & 3u) == 0;       // always true for torch generators
+    // offset % 4 == 0 (enforced by the launcher; torch's Philox offsets always are), so the
+    // WPT <= 4 draws of a byte are the four words of ONE block at counter (offset/4, k).
     const uint64_t blk = offset >> 2;
 #pragma unroll
     for (int c = 0; c < CHUNKS; ++c) {
+        const int col0 = (c * 32 + lane) * VEC;
+        if (FULL || col0 < F) {
+            uint4 ctr[VEC];
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-            const int col = (c * 32 + lane) * VEC + e;
-            if (FULL || col < F) {
-                float u[WPT];
-                const uint64_t k = kbase + (uint64_t)col;
-                if (fast_rng) byte_noise_fast<WPT>(keys, (uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)k, (uint32_t)(k >> 32), u);
-                else byte_noise<WPT>(seed, k, offset, u);
+            for (int e = 0; e < VEC; ++e) {
+                const uint64_t k = kbase + (uint64_t)(col0 + e);
+                ctr[e] = make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)k, (uint32_t)(k >> 32));
+            }
+            philox4x32_10_xN<VEC>(ctr, keys);          // VEC interleaved chains
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                const uint32_t w[4] = {ctr[e].x, ctr[e].y, ctr[e].z, ctr[e].w};
                 uint32_t byte = 0;
 #pragma unroll
                 for (int r = 0; r < WPT; ++r) {
                     if (FULL || r < nrows) {
-                        const int q = quantize_one(v[r][c][e], lo[r], scale[r], u[r]);
+                        const int q = quantize_one(v[r][c][e], lo[r], scale[r], uniform_from_u32(w[r]));
                         byte |= ((uint32_t)q << (r * BITS));
                     }
                 }
-                stage[phase16 + col] = (uint8_t)byte;
+                stage[phase16 + col0 + e] = (uint8_t)byte;
             }
         }
     }
@@ -185,6 +190,11 @@ send_quant_kernel(const float *__restrict__ x, int64_t ld, int F,
     const int wib = threadIdx.x >> 5;
     const int stage_stride = ((F + 16 + 15) >> 4) << 4;
     uint8_t *stage = smem + (size_t)wib * stage_stride;
+    // channel table in shared memory: a 30-cycle LDS instead of a dependent global load per item
+    adaqp_send_chan *s_chans = reinterpret_cast<adaqp_send_chan *>(smem + (size_t)kWarps * stage_stride);
+    for (int t = threadIdx.x; t < n_chans * (int)(sizeof(adaqp_send_chan) / 8); t += kThreads)
+        reinterpret_cast<uint64_t *>(s_chans)[t] = reinterpret_cast<const uint64_t *>(chans)[t];
+    __syncthreads();
     const int64_t warp = (int64_t)blockIdx.x * kWarps + wib;
     const int64_t nwarps = (int64_t)gridDim.x * kWarps;
     const float trace_coef = (float)((double)F / 6.0);
@@ -196,7 +206,7 @@ send_quant_kernel(const float *__restrict__ x, int64_t ld, int F,
             uint4 *q = reinterpret_cast<uint4 *>(&it);
             q[0] = __ldg(p); q[1] = __ldg(p + 1); q[2] = __ldg(p + 2); q[3] = __ldg(p + 3);
         }
-        const adaqp_send_chan ch = chans[it.chan];
+        const adaqp_send_chan ch = s_chans[it.chan];
         if (it.chan != acked) {
             // the peer must have consumed the previous payload of this key (seq - 1)
             bool ok = true;
@@ -208,8 +218,8 @@ send_quant_kernel(const float *__restrict__ x, int64_t ld, int F,
         const bool full = (F == 32 * VEC * CHUNKS) && (it.nrows * it.bits == 8);
 #define ADAQP_SEND(B)                                                                                          \
     do {                                                                                                       \
-        if (full) send_item<B, VEC, CHUNKS, true>(it, ch, x, ld, F, trace, trace_coef, keys, seed, base_offset, stage, lane);  \
-        else send_item<B, VEC, CHUNKS, false>(it, ch, x, ld, F, trace, trace_coef, keys, seed, base_offset, stage, lane);      \
+        if (full) send_item<B, VEC, CHUNKS, true>(it, ch, x, ld, F, trace, trace_coef, keys, base_offset, stage, lane);  \
+        else send_item<B, VEC, CHUNKS, false>(it, ch, x, ld, F, trace, trace_coef, keys, base_offset, stage, lane);      \
     } while (0)
         switch (it.bits) {
             case 2: ADAQP_SEND(2); break;
@@ -239,16 +249,30 @@ __device__ __forceinline__ void recv_item(const adaqp_recv_item &it, const adaqp
     constexpr uint32_t MASK = (1u << BITS) - 1u;
     const uint8_t *src = ch.qdata + it.src_off;
     const int nrows = it.nrows;
+    // 2/4-bit: a byte-row has only WPT * 2^BITS (= 16 / 32) distinct outputs val/scale + min.
+    // Lane (r * 2^BITS + val) computes that one value with the reference's IEEE division and
+    // add; every element is then a single shuffle lookup instead of a division.
+    constexpr int NV = 1 << BITS;
+    float lut = 0.f;
     float scale[WPT], mn[WPT], qz[WPT];
-#pragma unroll
-    for (int r = 0; r < WPT; ++r) {
-        if (r < nrows) {
-            scale[r] = bf16_bits_to_f32(__ldcg(ch.params + it.param_pos + r));
-            mn[r] = bf16_bits_to_f32(__ldcg(ch.params + ch.S + it.param_pos + r));
-        } else {
-            scale[r] = 1.f; mn[r] = 0.f;
+    if (BITS <= 4) {
+        const int lr = lane / NV, lv = lane % NV;
+        if (lr < nrows) {
+            const float sc = bf16_bits_to_f32(__ldcg(ch.params + it.param_pos + lr));
+            const float m = bf16_bits_to_f32(__ldcg(ch.params + ch.S + it.param_pos + lr));
+            lut = __fadd_rn(__fdiv_rn((float)lv, sc), m);
         }
-        qz[r] = __fdiv_rn(0.f, scale[r]);
+    } else {
+#pragma unroll
+        for (int r = 0; r < WPT; ++r) {
+            if (r < nrows) {
+                scale[r] = bf16_bits_to_f32(__ldcg(ch.params + it.param_pos + r));
+                mn[r] = bf16_bits_to_f32(__ldcg(ch.params + ch.S + it.param_pos + r));
+            } else {
+                scale[r] = 1.f; mn[r] = 0.f;
+            }
+            qz[r] = __fdiv_rn(0.f, scale[r]);
+        }
     }
     uint32_t bytes[CHUNKS][VEC];
     if (VEC == 4 && (reinterpret_cast<uintptr_t>(src) & 3u) == 0) {  // warp-uniform
@@ -276,14 +300,15 @@ __device__ __forceinline__ void recv_item(const adaqp_recv_item &it, const adaqp
 #pragma unroll
             for (int c = 0; c < CHUNKS; ++c) {
                 const int col = (c * 32 + lane) * VEC;
-                if (col < F) {
+                {
                     float o[VEC];
 #pragma unroll
                     for (int e = 0; e < VEC; ++e) {
                         const uint32_t ival = (bytes[c][e] >> (r * BITS)) & MASK;
-                        o[e] = __fadd_rn(dequant_div(ival, scale[r], qz[r]), mn[r]);  // IEEE div then add, as unpack
+                        if (BITS <= 4) o[e] = __shfl_sync(ADAQP_FULL_MASK, lut, r * NV + (int)ival);
+                        else o[e] = __fadd_rn(dequant_div(ival, scale[r], qz[r]), mn[r]);  // IEEE div then add, as unpack
                     }
-                    RowVec<VEC>::store(orow + col, o);
+                    if (col < F) RowVec<VEC>::store(orow + col, o);   // lanes past F still take part in the shuffles
                 }
             }
         }
@@ -296,6 +321,11 @@ recv_quant_kernel(float *__restrict__ halo, int64_t ld, int F,
                   const adaqp_recv_item *__restrict__ items, int64_t n_items,
                   const adaqp_recv_chan *__restrict__ chans, int n_chans, uint32_t seq,
                   uint32_t *work, uint32_t *status, uint64_t timeout_ns) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    adaqp_recv_chan *s_chans = reinterpret_cast<adaqp_recv_chan *>(smem);
+    for (int t = threadIdx.x; t < n_chans * (int)(sizeof(adaqp_recv_chan) / 8); t += kThreads)
+        reinterpret_cast<uint64_t *>(s_chans)[t] = reinterpret_cast<const uint64_t *>(chans)[t];
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * kWarps;
@@ -307,7 +337,7 @@ recv_quant_kernel(float *__restrict__ halo, int64_t ld, int F,
             uint4 *q = reinterpret_cast<uint4 *>(&it);
             q[0] = __ldg(p); q[1] = __ldg(p + 1);
         }
-        const adaqp_recv_chan ch = chans[it.chan];
+        const adaqp_recv_chan ch = s_chans[it.chan];
         if (it.chan != ready) {
             bool ok = true;
             if (lane == 0) ok = spin_wait_ge(ch.flag, seq, timeout_ns);
@@ -463,7 +493,9 @@ int adaqp_send_quant(const float *x, int64_t ld, int32_t F, const adaqp_send_ite
     const int vec = pick_vec(F, ld, x);
     const int nchunks = (F + 32 * vec - 1) / (32 * vec);
     const int stage_stride = ((F + 16 + 15) >> 4) << 4;
-    const size_t smem = (size_t)kWarps * stage_stride;
+    ADAQP_REQUIRE((base_offset & 3u) == 0, ADAQP_EINVAL, "adaqp_send_quant: base_offset must be a multiple of 4 (torch Philox offsets are)");
+    ADAQP_REQUIRE(n_chans <= 64, ADAQP_ELIMIT, "adaqp_send_quant: more than 64 channels");
+    const size_t smem = (size_t)kWarps * stage_stride + (size_t)n_chans * sizeof(adaqp_send_chan);
     const int grid = grid_for(n_items, 4);
     const PhiloxKeys keys = make_philox_keys(seed);
     cudaStream_t s = (cudaStream_t)stream;
@@ -506,10 +538,11 @@ int adaqp_recv_quant(float *halo, int64_t ld, int32_t F, const adaqp_recv_item *
     ADAQP_REQUIRE(chans && (n_items == 0 || (halo && items)), ADAQP_EINVAL, "adaqp_recv_quant: null pointer");
     const int vec = pick_vec(F, ld, halo);
     const int nchunks = (F + 32 * vec - 1) / (32 * vec);
+    ADAQP_REQUIRE(n_chans <= 64, ADAQP_ELIMIT, "adaqp_recv_quant: more than 64 channels");
     const int grid = grid_for(n_items, 8);
     cudaStream_t s = (cudaStream_t)stream;
 #define CALL_RECV(V, C)                                                                          \
-    recv_quant_kernel<V, C><<<grid, kThreads, 0, s>>>(halo, ld, F, items, n_items, chans, n_chans, \
+    recv_quant_kernel<V, C><<<grid, kThreads, (size_t)n_chans * sizeof(adaqp_recv_chan), s>>>(halo, ld, F, items, n_items, chans, n_chans, \
                                                       seq, work, status, timeout_ns)
     if (vec == 4) {
         if (nchunks <= 1) CALL_RECV(4, 1);
