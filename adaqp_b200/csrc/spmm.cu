@@ -54,7 +54,7 @@ spmm_csr_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ 
                 const float *__restrict__ x1, int64_t ld1,
                 const float *__restrict__ pre, const float *__restrict__ post,
                 int mean, int add_self, int64_t row_begin, int64_t row_end, int F,
-                float *__restrict__ out, int64_t ldo, unsigned long long *__restrict__ next_row) {
+                float *__restrict__ out, int64_t ldo, unsigned long long *__restrict__ next_row, int rows_per_grab) {
     const int lane = threadIdx.x & 31;
     bool colok[CHUNKS];
 #pragma unroll
@@ -69,10 +69,10 @@ spmm_csr_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ 
     const int64_t n_rows = row_end - row_begin;
     while (true) {
         unsigned long long grab = 0;
-        if (lane == 0) grab = atomicAdd(next_row, (unsigned long long)kRowsPerGrab);
+        if (lane == 0) grab = atomicAdd(next_row, (unsigned long long)rows_per_grab);
         grab = __shfl_sync(ADAQP_FULL_MASK, grab, 0);
         if ((int64_t)grab >= n_rows) break;
-        const int64_t r_hi = ((int64_t)grab + kRowsPerGrab < n_rows) ? (int64_t)grab + kRowsPerGrab : n_rows;
+        const int64_t r_hi = ((int64_t)grab + rows_per_grab < n_rows) ? (int64_t)grab + rows_per_grab : n_rows;
     for (int64_t row = row_begin + (int64_t)grab; row < row_begin + r_hi; ++row) {
         float acc[CHUNKS][VEC];
 #pragma unroll
@@ -372,6 +372,13 @@ int adaqp_spmm_csr_f32(const int64_t *indptr, const int32_t *indices, const floa
         else launch(spmm_csr_ring_kernel<8>, 8);
         return adaqp_check_launch("spmm_csr_ring_kernel");
     }
+    static int grab_rows = -1;
+    if (grab_rows < 0) { const char *e = getenv("ADAQP_SPMM_GRAB"); grab_rows = e ? atoi(e) : 0; }
+    // measured on B200 (profiles/r01_spmm_frontier.md): 1 row per grab for wide rows, 2 for F <= 128
+    const int grab_now = grab_rows > 0 ? grab_rows : (F > 128 ? 1 : 2);
+    static int ctas_sm = -1;
+    if (ctas_sm < 0) { const char *e = getenv("ADAQP_SPMM_CTAS"); ctas_sm = e ? atoi(e) : 8; if (ctas_sm < 1) ctas_sm = 1; }
+    { const int64_t cap2 = (int64_t)sms * ctas_sm; if (grid > cap2) grid = cap2; }
     // per-launch row counter from a small rotating pool (stream-ordered reset)
     static unsigned long long *pool = nullptr;
     static unsigned pool_pos = 0;
@@ -382,7 +389,7 @@ int adaqp_spmm_csr_f32(const int64_t *indptr, const int32_t *indices, const floa
 #define CALL_SPMM(V, C)                                                                           \
     spmm_csr_kernel<V, C><<<(unsigned)grid, kThreads, 0, s>>>(indptr, indices, x0, ld0, n_split, x1, \
                                                              ld1, pre, post, mean, add_self,      \
-                                                             row_begin, row_end, F, out, ldo, counter)
+                                                             row_begin, row_end, F, out, ldo, counter, grab_now)
     if (vec == 4) {
         if (nchunks <= 1) CALL_SPMM(4, 1);
         else if (nchunks <= 2) CALL_SPMM(4, 2);
