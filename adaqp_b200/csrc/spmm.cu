@@ -54,7 +54,8 @@ spmm_csr_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ 
                 const float *__restrict__ x1, int64_t ld1,
                 const float *__restrict__ pre, const float *__restrict__ post,
                 int mean, int add_self, int64_t row_begin, int64_t row_end, int F,
-                float *__restrict__ out, int64_t ldo, unsigned long long *__restrict__ next_row, int rows_per_grab) {
+                float *__restrict__ out, int64_t ldo, unsigned long long *__restrict__ next_row, int rows_per_grab,
+                const int64_t *__restrict__ seg_start, const int64_t *__restrict__ seg_end, int accumulate) {
     const int lane = threadIdx.x & 31;
     bool colok[CHUNKS];
 #pragma unroll
@@ -79,7 +80,11 @@ spmm_csr_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ 
         for (int c = 0; c < CHUNKS; ++c)
 #pragma unroll
             for (int e = 0; e < VEC; ++e) acc[c][e] = 0.f;
-        const int64_t b = __ldg(indptr + row), e_ = __ldg(indptr + row + 1);
+        // neighbour segment of this launch: the whole row, or [seg_start[row], seg_end[row]) when the
+        // caller splits a row into its local-source and halo-source parts (ops.py overlap)
+        const int64_t row_b = __ldg(indptr + row), row_e = __ldg(indptr + row + 1);
+        const int64_t b = seg_start ? __ldg(seg_start + row) : row_b;
+        const int64_t e_ = seg_end ? __ldg(seg_end + row) : row_e;
         for (int64_t j0 = b; j0 < e_; j0 += 32) {
             const int n = (e_ - j0) < 32 ? (int)(e_ - j0) : 32;
             int u = 0;
@@ -130,17 +135,20 @@ spmm_csr_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ 
                 }
             }
         }
-        const float deg = (float)(e_ - b);
+        const float deg = (float)(row_e - row_b);       // mean divides by the full in-degree
         const float ps = post ? __ldg(post + row) : 1.f;
         float *orow = out + (row - row_begin) * ldo;
 #pragma unroll
         for (int c = 0; c < CHUNKS; ++c) {
             if (colok[c]) {
+                float prev[VEC];
+                if (accumulate) Vec<VEC>::load(orow + (c * 32 + lane) * VEC, prev);
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) {
                     float r = acc[c][e];
                     if (mean && deg > 0.f) r = __fdiv_rn(r, deg);
                     if (post) r = __fmul_rn(r, ps);
+                    if (accumulate) r = __fadd_rn(prev[e], r);
                     acc[c][e] = r;
                 }
                 Vec<VEC>::store(orow + (c * 32 + lane) * VEC, acc[c]);
@@ -324,10 +332,11 @@ inline bool aligned(const void *p, int vec) { return ((uintptr_t)p & ((uintptr_t
 
 extern "C" {
 
-int adaqp_spmm_csr_f32(const int64_t *indptr, const int32_t *indices, const float *x0, int64_t ld0,
-                       int64_t n_split, const float *x1, int64_t ld1, const float *pre,
-                       const float *post, int mean, int add_self, int64_t row_begin,
-                       int64_t row_end, int32_t F, float *out, int64_t ldo, void *stream) {
+int adaqp_spmm_csr_seg_f32(const int64_t *indptr, const int64_t *seg_start, const int64_t *seg_end,
+                           const int32_t *indices, const float *x0, int64_t ld0,
+                           int64_t n_split, const float *x1, int64_t ld1, const float *pre,
+                           const float *post, int mean, int add_self, int accumulate, int64_t row_begin,
+                           int64_t row_end, int32_t F, float *out, int64_t ldo, void *stream) {
     ADAQP_REQUIRE(F > 0 && F <= 1024, ADAQP_ELIMIT, "adaqp_spmm_csr_f32: F=%d outside (0,1024]", F);
     ADAQP_REQUIRE(row_end >= row_begin && row_begin >= 0, ADAQP_EINVAL, "adaqp_spmm_csr_f32: bad row range");
     if (row_end == row_begin) return 0;
@@ -350,7 +359,7 @@ int adaqp_spmm_csr_f32(const int64_t *indptr, const int32_t *indices, const floa
     // v2 (cp.async ring) needs 16-byte rows: F % 4 == 0, strides % 4 == 0, 16-byte aligned bases
     static int impl = -1;
     if (impl < 0) { const char *e = getenv("ADAQP_SPMM"); impl = (e && e[0] == '2') ? 2 : 1; }   // default v1
-    if (impl == 2 && vec == 4 && nchunks <= 8) {
+    if (impl == 2 && vec == 4 && nchunks <= 8 && !seg_start && !seg_end && !accumulate) {
         auto launch = [&](auto kernel, int C) {
             const size_t smem = (size_t)kWarps * kStages * C * 512;
             int ctas_per_sm = (int)((200 * 1024) / (smem + 1024));
@@ -389,7 +398,7 @@ int adaqp_spmm_csr_f32(const int64_t *indptr, const int32_t *indices, const floa
 #define CALL_SPMM(V, C)                                                                           \
     spmm_csr_kernel<V, C><<<(unsigned)grid, kThreads, 0, s>>>(indptr, indices, x0, ld0, n_split, x1, \
                                                              ld1, pre, post, mean, add_self,      \
-                                                             row_begin, row_end, F, out, ldo, counter, grab_now)
+                                                             row_begin, row_end, F, out, ldo, counter, grab_now, seg_start, seg_end, accumulate)
     if (vec == 4) {
         if (nchunks <= 1) CALL_SPMM(4, 1);
         else if (nchunks <= 2) CALL_SPMM(4, 2);
@@ -411,6 +420,15 @@ int adaqp_spmm_csr_f32(const int64_t *indptr, const int32_t *indices, const floa
     }
 #undef CALL_SPMM
     return adaqp_check_launch("spmm_csr_kernel");
+}
+
+
+int adaqp_spmm_csr_f32(const int64_t *indptr, const int32_t *indices, const float *x0, int64_t ld0,
+                       int64_t n_split, const float *x1, int64_t ld1, const float *pre,
+                       const float *post, int mean, int add_self, int64_t row_begin,
+                       int64_t row_end, int32_t F, float *out, int64_t ldo, void *stream) {
+    return adaqp_spmm_csr_seg_f32(indptr, nullptr, nullptr, indices, x0, ld0, n_split, x1, ld1, pre, post, mean,
+                                  add_self, 0, row_begin, row_end, F, out, ldo, stream);
 }
 
 }  // extern "C"

@@ -23,6 +23,12 @@ class LocalGraph(object):
         self.indptr = torch.from_numpy(np.ascontiguousarray(indptr, np.int64)).to(self.device)
         self.indices = torch.from_numpy(np.ascontiguousarray(indices, np.int32)).to(self.device)
         self.nnz = int(self.indices.numel())
+        # first halo column of every row (columns are sorted, halo ids >= n_inner): lets the
+        # aggregation of a row be split into its local-source and halo-source segments
+        ip = np.ascontiguousarray(indptr, np.int64)
+        is_local = (np.asarray(indices) < self.n_inner)
+        csum = np.concatenate([[0], np.cumsum(is_local, dtype=np.int64)])
+        self.halo_split = torch.from_numpy(ip[:-1] + (csum[ip[1:]] - csum[ip[:-1]])).to(self.device)
         self.ndata: Dict[str, torch.Tensor] = {
             "in_degrees": torch.from_numpy(np.ascontiguousarray(in_degrees)).to(self.device),
             "out_degrees": torch.from_numpy(np.ascontiguousarray(out_degrees)).to(self.device),
@@ -48,8 +54,10 @@ class LocalGraph(object):
 def spmm(graph: LocalGraph, x_local: torch.Tensor, x_halo: Optional[torch.Tensor],
          pre: Optional[torch.Tensor], post: Optional[torch.Tensor], mean: bool = False,
          add_self: bool = False, row_begin: int = 0, row_end: Optional[int] = None,
-         out: Optional[torch.Tensor] = None, stream=None) -> torch.Tensor:
-    """out[v - row_begin] = post[v] * sum_u pre[u] x[u]  over the CSR rows [row_begin, row_end)."""
+         out: Optional[torch.Tensor] = None, stream=None, part: Optional[str] = None) -> torch.Tensor:
+    """out[v - row_begin] = post[v] * sum_u pre[u] x[u]  over the CSR rows [row_begin, row_end).
+    part='local': only the local-source neighbours of each row (no halo needed);
+    part='halo' : only the halo-source neighbours, ACCUMULATED into `out`."""
     L = _lib.load()
     row_end = graph.n_inner if row_end is None else int(row_end)
     F = int(x_local.shape[1])
@@ -58,12 +66,22 @@ def spmm(graph: LocalGraph, x_local: torch.Tensor, x_halo: Optional[torch.Tensor
         out = torch.empty((row_end - row_begin, F), dtype=torch.float32, device=x_local.device)
     if x_halo is not None and x_halo.shape[0] == 0:
         x_halo = None
-    rc = L.adaqp_spmm_csr_f32(
-        graph.indptr.data_ptr(), graph.indices.data_ptr(), x_local.data_ptr(), x_local.stride(0),
-        graph.n_inner, x_halo.data_ptr() if x_halo is not None else None,
+    seg_start = seg_end = None
+    accumulate = 0
+    if part == "local":
+        seg_end = graph.halo_split.data_ptr()
+    elif part == "halo":
+        assert out is not None, "the halo part accumulates into the output of the local part"
+        seg_start = graph.halo_split.data_ptr()
+        accumulate, add_self = 1, False
+    elif part is not None:
+        raise ValueError(part)
+    rc = L.adaqp_spmm_csr_seg_f32(
+        graph.indptr.data_ptr(), seg_start, seg_end, graph.indices.data_ptr(), x_local.data_ptr(),
+        x_local.stride(0), graph.n_inner, x_halo.data_ptr() if x_halo is not None else None,
         x_halo.stride(0) if x_halo is not None else 0,
         pre.data_ptr() if pre is not None else None, post.data_ptr() if post is not None else None,
-        1 if mean else 0, 1 if add_self else 0, int(row_begin), row_end, F, out.data_ptr(),
+        1 if mean else 0, 1 if add_self else 0, accumulate, int(row_begin), row_end, F, out.data_ptr(),
         out.stride(0), _lib.stream_ptr(stream))
-    _lib.check(rc, "adaqp_spmm_csr_f32")
+    _lib.check(rc, "adaqp_spmm_csr_seg_f32")
     return out

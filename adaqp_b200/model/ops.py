@@ -33,9 +33,10 @@ def _split(graph, feats: Tensor, x_halo: Tensor = None):
     return g, feats, x_halo
 
 
-def _run(g, x_local, x_halo, pre, post, mean, add_self, lo, hi, out=None):
+def _run(g, x_local, x_halo, pre, post, mean, add_self, lo, hi, out=None, part=None):
     if isinstance(g, LocalGraph):
-        return spmm(g, x_local, x_halo, pre, post, mean=mean, add_self=add_self, row_begin=lo, row_end=hi, out=out)
+        return spmm(g, x_local, x_halo, pre, post, mean=mean, add_self=add_self, row_begin=lo, row_end=hi, out=out,
+                    part=part)
     from ..manager.graph_cpu import spmm_cpu          # gloo plumbing mode
     res = spmm_cpu(g, x_local, x_halo, pre, post, mean=mean, add_self=add_self, row_begin=lo, row_end=hi)
     if out is not None:
@@ -45,7 +46,7 @@ def _run(g, x_local, x_halo, pre, post, mean, add_self, lo, hi, out=None):
 
 
 def GCN_aggregation(graph, feats: Tensor, mode: ProprogationMode = ProprogationMode.Forward,
-                    x_halo: Tensor = None, out: Tensor = None) -> Tensor:
+                    x_halo: Tensor = None, out: Tensor = None, part: str = None) -> Tensor:
     """out[v] = norm2[v] * sum_{u->v} norm1[u] x[u] with global-degree norms (ops.py:17-32).
     `feats` may be cat(local, halo) as in the reference, or the local rows with `x_halo`."""
     g, x_local, x_halo = _split(graph, feats, x_halo)
@@ -56,35 +57,36 @@ def GCN_aggregation(graph, feats: Tensor, mode: ProprogationMode = ProprogationM
         pre, post = g.norm["in_-0.5"], g.norm["out_-0.5"]
     else:
         raise ValueError(f"Invalid mode {mode}")
-    return _run(g, x_local, x_halo, pre, post, False, False, lo, hi, out)
+    return _run(g, x_local, x_halo, pre, post, False, False, lo, hi, out, part)
 
 
 def SAGE_aggregation(graph, feats: Tensor, mode: ProprogationMode = ProprogationMode.Forward,
-                     aggregator_type="mean", x_halo: Tensor = None, out: Tensor = None) -> Tensor:
+                     aggregator_type="mean", x_halo: Tensor = None, out: Tensor = None, part: str = None) -> Tensor:
     """ops.py:34-67: 'mean' = mean over in-neighbours (fwd) / sum of x[u]/outdeg[u] (bwd);
     'gcn' = (sum + self) / (indeg + 1) (fwd) / sum + self of x/(outdeg+1) (bwd)."""
     g, x_local, x_halo = _split(graph, feats, x_halo)
     lo, hi = (graph.begin, graph.end) if isinstance(graph, RowRange) else (0, g.n_inner)
     if mode == ProprogationMode.Forward:
         if aggregator_type == "mean":
-            return _run(g, x_local, x_halo, None, None, True, False, lo, hi, out)
+            return _run(g, x_local, x_halo, None, None, True, False, lo, hi, out, part)
         if aggregator_type == "gcn":
-            return _run(g, x_local, x_halo, None, g.norm["in_+1_-1"], False, True, lo, hi, out)
+            return _run(g, x_local, x_halo, None, g.norm["in_+1_-1"], False, True, lo, hi, out, part)
     elif mode == ProprogationMode.Backward:
         if aggregator_type == "mean":
-            return _run(g, x_local, x_halo, g.norm["out_-1"], None, False, False, lo, hi, out)
+            return _run(g, x_local, x_halo, g.norm["out_-1"], None, False, False, lo, hi, out, part)
         if aggregator_type == "gcn":
-            return _run(g, x_local, x_halo, g.norm["out_+1_-1"], None, False, True, lo, hi, out)
+            return _run(g, x_local, x_halo, g.norm["out_+1_-1"], None, False, True, lo, hi, out, part)
     else:
         raise ValueError(f"Invalid mode {mode}")
     raise ValueError(f"Invalid aggregator_type {aggregator_type}")
 
 
-def _aggregate(class_name: str, graph, x_local, x_halo, mode, out):
+def _aggregate(class_name: str, graph, x_local, x_halo, mode, out, part=None):
     if class_name == "DistAggConv":
-        return GCN_aggregation(graph, x_local, mode=mode, x_halo=x_halo, out=out)
+        return GCN_aggregation(graph, x_local, mode=mode, x_halo=x_halo, out=out, part=part)
     if class_name == "DistAggSAGE":
-        return SAGE_aggregation(graph, x_local, mode=mode, aggregator_type=engine.ctx.agg_type, x_halo=x_halo, out=out)
+        return SAGE_aggregation(graph, x_local, mode=mode, aggregator_type=engine.ctx.agg_type, x_halo=x_halo, out=out,
+                                part=part)
     raise ValueError(f"Invalid class_name {class_name}")
 
 
@@ -176,12 +178,16 @@ def decomposed_graph_propagation(ctx, local_messages: Tensor, graph, layer: int,
     out = local_messages.new_empty((eng.num_inner, local_messages.shape[1]))
     with timer.record_events(f"{name}_central_aggregation"):
         _aggregate(class_name, graph.central_graph, local_messages, None, mode, out[:eng.num_central])
-    central_done = torch.cuda.Event(enable_timing=True)
-    central_done.record(main)
-    timer.record_exposed(name, central_done, landed)
+    # the marginal rows' LOCAL-source neighbours do not need the halo either: aggregate them while
+    # the exchange is still in flight; only the halo-source segment of each row waits for it
+    with timer.record_events(f"{name}_marginal_aggregation_local"):
+        _aggregate(class_name, graph.marginal_graph, local_messages, None, mode, out[eng.num_central:], part="local")
+    overlappable_done = torch.cuda.Event(enable_timing=True)
+    overlappable_done.record(main)
+    timer.record_exposed(name, overlappable_done, landed)
     main.wait_event(landed)
-    with timer.record_events(f"{name}_marginal_aggregation"):
-        _aggregate(class_name, graph.marginal_graph, local_messages, pend.halo, mode, out[eng.num_central:])
+    with timer.record_events(f"{name}_marginal_aggregation_halo"):
+        _aggregate(class_name, graph.marginal_graph, local_messages, pend.halo, mode, out[eng.num_central:], part="halo")
     pend.release()
     local_messages.record_stream(side)
     return _finish(ctx, out, layer, mode)

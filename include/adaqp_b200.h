@@ -199,6 +199,19 @@ int adaqp_spmm_csr_f32(const int64_t *indptr, const int32_t *indices,
                        int64_t row_begin, int64_t row_end, int32_t F,
                        float *out, int64_t ldo, void *stream);
 
+/* Same aggregation over a per-row neighbour SEGMENT [seg_start[v], seg_end[v]) of the CSR row
+ * (NULL = the row's own bounds), optionally accumulating into `out` (out += ...).  With the
+ * columns of a row sorted, [indptr[v], split[v]) are the local sources and [split[v],
+ * indptr[v+1]) the halo sources: the local part of the marginal rows can then run while the
+ * exchange is still in flight and only the halo part waits for it (a finer overlap than the
+ * reference's central / marginal split, ops.py:156-193).  `mean` still divides by the full
+ * in-degree indptr[v+1] - indptr[v]; add_self belongs to exactly one of the two calls. */
+int adaqp_spmm_csr_seg_f32(const int64_t *indptr, const int64_t *seg_start, const int64_t *seg_end,
+                           const int32_t *indices, const float *x0, int64_t ld0, int64_t n_split,
+                           const float *x1, int64_t ld1, const float *pre, const float *post,
+                           int mean, int add_self, int accumulate, int64_t row_begin,
+                           int64_t row_end, int32_t F, float *out, int64_t ldo, void *stream);
+
 /* Row gather out[i] = x[idx[i]] (copy-buffer fills of ops.py:159-164; API parity only). */
 int adaqp_gather_rows_f32(const float *x, int64_t ld, const int64_t *idx, int64_t n,
                           int32_t F, float *out, int64_t ldo, void *stream);
