@@ -20,6 +20,7 @@ cross edge agree.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field, asdict
 from typing import Dict, List, Optional, Tuple
 
@@ -67,6 +68,7 @@ def spec_from_config(config: dict, num_parts: int, scale: float = 1.0) -> SynthS
                      degree_exponent=float(s.get("degree_exponent", 2.3)),
                      community_size=int(s.get("community_size", 4096)),
                      homophily=float(s.get("homophily", 0.6)),
+                     feature_signal=float(os.environ.get("ADAQP_SYNTH_SIGNAL", s.get("feature_signal", 0.5))),
                      train_fraction=float(s["train_fraction"]), val_fraction=float(s["val_fraction"]),
                      seed=int(s.get("seed", 0)))
     return spec.scaled(scale) if scale != 1.0 else spec

@@ -47,8 +47,10 @@ def main():
     ap.add_argument("--model_name", type=str, default="gcn")
     ap.add_argument("--assign_cycle", type=int, default=25)
     ap.add_argument("--json", type=str, default=None)
+    ap.add_argument("--signal", type=float, default=0.12, help="class-centroid strength of the synthetic features")
     args = ap.parse_args()
     os.environ["ADAQP_SYNTH_SCALE"] = str(args.scale)
+    os.environ["ADAQP_SYNTH_SIGNAL"] = str(args.signal)
     os.environ.setdefault("ADAQP_SEED", "123")
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     import __graft_entry__ as entry
@@ -61,7 +63,7 @@ def main():
             print(json.dumps(out[-1]), flush=True)
     if rank == 0:
         base = out[0]["best_val"]
-        summary = {"world": world, "epochs": args.epochs, "scale": args.scale, "model": args.model_name, "runs": out,
+        summary = {"world": world, "epochs": args.epochs, "scale": args.scale, "feature_signal": args.signal, "model": args.model_name, "runs": out,
                    "delta_best_val_vs_vanilla_pct": {f"{o['mode']}/{o['scheme']}": 100 * (o["best_val"] - base) for o in out[1:]}}
         print(json.dumps(summary), flush=True)
         if args.json:
