@@ -120,6 +120,20 @@ class DistAggSAGE(Function):
                   ProprogationMode.Backward, DistAggSAGE.__name__)
 
 
+_SPLIT = None
+
+
+def _split_marginal() -> bool:
+    """ADAQP_MARGINAL_SPLIT=1: two-pass marginal aggregation (local sources overlap the exchange, the
+    halo sources accumulate afterwards).  Removes the exposed wait at the price of a second pass over
+    the marginal rows; measured both ways in profiles/r01_overlap.md."""
+    global _SPLIT
+    if _SPLIT is None:
+        import os
+        _SPLIT = os.environ.get("ADAQP_MARGINAL_SPLIT", "0") == "1"
+    return _SPLIT
+
+
 def _finish(ctx, out: Tensor, layer: int, mode: ProprogationMode):
     if mode == ProprogationMode.Forward:
         ctx.saved = layer
@@ -178,16 +192,24 @@ def decomposed_graph_propagation(ctx, local_messages: Tensor, graph, layer: int,
     out = local_messages.new_empty((eng.num_inner, local_messages.shape[1]))
     with timer.record_events(f"{name}_central_aggregation"):
         _aggregate(class_name, graph.central_graph, local_messages, None, mode, out[:eng.num_central])
-    # the marginal rows' LOCAL-source neighbours do not need the halo either: aggregate them while
-    # the exchange is still in flight; only the halo-source segment of each row waits for it
-    with timer.record_events(f"{name}_marginal_aggregation_local"):
-        _aggregate(class_name, graph.marginal_graph, local_messages, None, mode, out[eng.num_central:], part="local")
-    overlappable_done = torch.cuda.Event(enable_timing=True)
-    overlappable_done.record(main)
-    timer.record_exposed(name, overlappable_done, landed)
-    main.wait_event(landed)
-    with timer.record_events(f"{name}_marginal_aggregation_halo"):
-        _aggregate(class_name, graph.marginal_graph, local_messages, pend.halo, mode, out[eng.num_central:], part="halo")
+    if _split_marginal():
+        # the marginal rows' LOCAL-source neighbours do not need the halo either: aggregate them while
+        # the exchange is still in flight; only the halo-source segment of each row waits for it
+        with timer.record_events(f"{name}_marginal_aggregation_local"):
+            _aggregate(class_name, graph.marginal_graph, local_messages, None, mode, out[eng.num_central:], part="local")
+        overlappable_done = torch.cuda.Event(enable_timing=True)
+        overlappable_done.record(main)
+        timer.record_exposed(name, overlappable_done, landed)
+        main.wait_event(landed)
+        with timer.record_events(f"{name}_marginal_aggregation_halo"):
+            _aggregate(class_name, graph.marginal_graph, local_messages, pend.halo, mode, out[eng.num_central:], part="halo")
+    else:
+        central_done = torch.cuda.Event(enable_timing=True)
+        central_done.record(main)
+        timer.record_exposed(name, central_done, landed)
+        main.wait_event(landed)
+        with timer.record_events(f"{name}_marginal_aggregation"):
+            _aggregate(class_name, graph.marginal_graph, local_messages, pend.halo, mode, out[eng.num_central:])
     pend.release()
     local_messages.record_stream(side)
     return _finish(ctx, out, layer, mode)

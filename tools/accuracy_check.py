@@ -47,7 +47,7 @@ def main():
     ap.add_argument("--model_name", type=str, default="gcn")
     ap.add_argument("--assign_cycle", type=int, default=25)
     ap.add_argument("--json", type=str, default=None)
-    ap.add_argument("--signal", type=float, default=0.12, help="class-centroid strength of the synthetic features")
+    ap.add_argument("--feature-signal", dest="signal", type=float, default=0.12, help="class-centroid strength of the synthetic features")
     args = ap.parse_args()
     os.environ["ADAQP_SYNTH_SCALE"] = str(args.scale)
     os.environ["ADAQP_SYNTH_SIGNAL"] = str(args.signal)
