@@ -124,13 +124,14 @@ _SPLIT = None
 
 
 def _split_marginal() -> bool:
-    """ADAQP_MARGINAL_SPLIT=1: two-pass marginal aggregation (local sources overlap the exchange, the
-    halo sources accumulate afterwards).  Removes the exposed wait at the price of a second pass over
-    the marginal rows; measured both ways in profiles/r01_overlap.md."""
+    """Two-pass marginal aggregation (default; ADAQP_MARGINAL_SPLIT=0 restores the reference's
+    single pass): local sources overlap the exchange, the halo sources accumulate afterwards.
+    Removes the exposed wait at the price of a second pass over the marginal rows; measured
+    both ways in profiles/r01_overlap.md."""
     global _SPLIT
     if _SPLIT is None:
         import os
-        _SPLIT = os.environ.get("ADAQP_MARGINAL_SPLIT", "0") == "1"
+        _SPLIT = os.environ.get("ADAQP_MARGINAL_SPLIT", "1") != "0"
     return _SPLIT
 
 
