@@ -44,6 +44,16 @@ def _worker(rank, world, port, tmp, mode, model_name, out):
     for p, idx in eng.recv_idx.items():
         lo, hi = gathered[p]["send_idx"][rank]
         assert torch.allclose(remote[idx].sum(1), gathered[p]["send_rows"][lo:hi])
+    # evaluation forward: layer 0 (constant features, fp32 exchange) is computed once and reused
+    tr.model.eval()
+    with torch.no_grad():
+        a = tr.model(eng.graph, eng.feats)
+        eng.timer.clear(is_train=False)
+        b = tr.model(eng.graph, eng.feats)
+    assert torch.equal(a, b)
+    assert not any(k.startswith("forward0") for k in list(eng.timer._record) + list(eng.timer._events))
+    assert any(k.startswith("forward1") for k in list(eng.timer._record) + list(eng.timer._events))
+    eng.timer.clear(is_train=False)
     rec = tr.train()
     tr.save(rec)
     losses_ok = bool(torch.isfinite(rec).all())
