@@ -191,6 +191,85 @@ class QuantPlan:
     wire: Dict[int, Tuple[int, int]]   # src peer -> (qdata bytes, rows) of the reference wire format
 
 
+def build_send_items(send_peers: Sequence[int], send_idx: Dict[int, Tuple[int, int]], total_send_idx: np.ndarray,
+                     bits_by_peer: Dict[int, np.ndarray], F: int) -> Tuple[np.ndarray, int]:
+    """Sender work items of one layer key (pure host code, unit-tested against the oracle's wire
+    layout): for each peer in dict order, for each bit-width in (2, 4, 8) with rows, one item per
+    byte-row.  Mirrors the loop nest of op_util.py:194-209 / buffer.py:195-204: segment k of a
+    peer starts at the sum of the previous segments' qsize (payload + 1 unwritten byte), its rows
+    are the ascending local ids with that bit-width, and every segment consumes one
+    philox_engine_inputs(F * 8/bits) of the generator.  Returns (items, total generator advance)."""
+    items: List[np.ndarray] = []
+    rel = 0
+    for ci, p in enumerate(send_peers):
+        lo, hi = send_idx[p]
+        bits_p = np.asarray(bits_by_peer[p])
+        assert bits_p.size == hi - lo
+        seg_off = prm_off = 0
+        for b in BITS_SET:
+            ids = np.nonzero(bits_p == b)[0]          # ascending local ids (torch.nonzero)
+            if ids.size == 0:
+                continue
+            wpt = 8 // b
+            g = (ids.size + wpt - 1) // wpt
+            it = np.zeros(g, _lib.SEND_ITEM_DTYPE)
+            pos = np.full(g * wpt, -1, np.int64)
+            pos[:ids.size] = lo + ids
+            pos = pos.reshape(g, wpt)
+            it["send_pos"][:, :wpt] = pos
+            it["send_pos"][:, wpt:] = -1
+            it["src_row"][:, :wpt] = np.where(pos >= 0, total_send_idx[np.maximum(pos, 0)], -1)
+            it["src_row"][:, wpt:] = -1
+            it["dst_off"] = seg_off + np.arange(g, dtype=np.int64) * F
+            it["param_pos"] = prm_off + np.arange(g, dtype=np.int64) * wpt
+            it["group"] = np.arange(g)
+            it["rel_offset"] = rel
+            it["chan"] = ci
+            it["bits"] = b
+            it["nrows"] = np.minimum(wpt, ids.size - np.arange(g) * wpt)
+            items.append(it)
+            seg_off += qsize(ids.size, b, F)
+            prm_off += ids.size
+            rel += ((F * wpt + 3) // 4) * 4          # philox_engine_inputs rounding
+    out = np.concatenate(items) if items else np.zeros(0, _lib.SEND_ITEM_DTYPE)
+    return out, rel
+
+
+def build_recv_items(recv_peers: Sequence[int], recv_idx: Dict[int, np.ndarray], bits_from_peer: Dict[int, np.ndarray],
+                     F: int) -> Tuple[np.ndarray, Dict[int, Tuple[int, int]]]:
+    """Receiver work items (op_util.py:216-235): segment layout as on the sender; row j of a segment
+    lands at halo row recv_idx[p][orig_ids[j]].  Returns (items, {peer: (wire bytes, rows)})."""
+    items: List[np.ndarray] = []
+    wire: Dict[int, Tuple[int, int]] = {}
+    for ci, p in enumerate(recv_peers):
+        bits_p = np.asarray(bits_from_peer[p])
+        ridx = np.asarray(recv_idx[p])
+        assert bits_p.size == ridx.size
+        seg_off = prm_off = 0
+        for b in BITS_SET:
+            ids = np.nonzero(bits_p == b)[0]
+            if ids.size == 0:
+                continue
+            wpt = 8 // b
+            g = (ids.size + wpt - 1) // wpt
+            it = np.zeros(g, _lib.RECV_ITEM_DTYPE)
+            dst = np.full(g * wpt, -1, np.int64)
+            dst[:ids.size] = ridx[ids]                # remote[recv_idx[p]][orig_ids]
+            it["dst_row"][:, :wpt] = dst.reshape(g, wpt)
+            it["dst_row"][:, wpt:] = -1
+            it["src_off"] = seg_off + np.arange(g, dtype=np.int64) * F
+            it["param_pos"] = prm_off + np.arange(g, dtype=np.int64) * wpt
+            it["chan"] = ci
+            it["bits"] = b
+            it["nrows"] = np.minimum(wpt, ids.size - np.arange(g) * wpt)
+            items.append(it)
+            seg_off += qsize(ids.size, b, F)
+            prm_off += ids.size
+        wire[p] = (seg_off, int(ridx.size))
+    out = np.concatenate(items) if items else np.zeros(0, _lib.RECV_ITEM_DTYPE)
+    return out, wire
+
+
 class PeerExchange:
     """Data plane of one rank.
 
@@ -319,87 +398,28 @@ class PeerExchange:
         mine = metas[me]
         for key in mine:
             F = self.dims[key]
-            # ---------------- sender tables
-            s_items: List[np.ndarray] = []
             chans = np.zeros(len(self.send_peers), _lib.SEND_CHAN_DTYPE)
-            rel = 0
             for ci, p in enumerate(self.send_peers):
                 lo, hi = self.send_idx[p]
-                bits_p = np.asarray(mine[key][p])
-                assert bits_p.size == hi - lo
                 lay_p = self.layouts[p]
                 chans[ci]["qdata"] = self.peer_base[p] + lay_p.qdata_off[(key, me)]
                 chans[ci]["params"] = self.peer_base[p] + lay_p.params_off[(key, me)]
                 chans[ci]["flag"] = self.peer_base[p] + lay_p.flag_off[key] + 4 * me
                 chans[ci]["ack"] = self.slab.ptr + self.layout.ack_off[key] + 4 * p
                 chans[ci]["S"] = hi - lo
-                seg_off = 0
-                prm_off = 0
-                for b in BITS_SET:
-                    ids = np.nonzero(bits_p == b)[0]          # ascending local ids (torch.nonzero)
-                    if ids.size == 0:
-                        continue
-                    wpt = 8 // b
-                    g = (ids.size + wpt - 1) // wpt
-                    it = np.zeros(g, _lib.SEND_ITEM_DTYPE)
-                    pos = np.full(g * wpt, -1, np.int64)
-                    pos[:ids.size] = lo + ids
-                    pos = pos.reshape(g, wpt)
-                    it["send_pos"][:, :wpt] = pos
-                    it["send_pos"][:, wpt:] = -1
-                    rows = np.where(pos >= 0, self.total_send_idx[np.maximum(pos, 0)], -1)
-                    it["src_row"][:, :wpt] = rows
-                    it["src_row"][:, wpt:] = -1
-                    it["dst_off"] = seg_off + np.arange(g, dtype=np.int64) * F
-                    it["param_pos"] = prm_off + np.arange(g, dtype=np.int64) * wpt
-                    it["group"] = np.arange(g)
-                    it["rel_offset"] = rel
-                    it["chan"] = ci
-                    it["bits"] = b
-                    it["nrows"] = np.minimum(wpt, ids.size - np.arange(g) * wpt)
-                    s_items.append(it)
-                    seg_off += qsize(ids.size, b, F)
-                    prm_off += ids.size
-                    rel += ((F * wpt + 3) // 4) * 4          # philox_engine_inputs rounding
-            send_items = np.concatenate(s_items) if s_items else np.zeros(0, _lib.SEND_ITEM_DTYPE)
+            send_items, rel = build_send_items(self.send_peers, self.send_idx, self.total_send_idx,
+                                               {p: np.asarray(mine[key][p]) for p in self.send_peers}, F)
             compat = send_items.copy()
             compat["src_row"] = compat["send_pos"]
-            # ---------------- receiver tables
-            r_items: List[np.ndarray] = []
             rchans = np.zeros(len(self.recv_peers), _lib.RECV_CHAN_DTYPE)
-            wire: Dict[int, Tuple[int, int]] = {}
             for ci, p in enumerate(self.recv_peers):
-                bits_p = np.asarray(metas[p][key][me])
-                ridx = self.recv_idx[p]
-                assert bits_p.size == ridx.size
                 rchans[ci]["qdata"] = self.slab.ptr + self.layout.qdata_off[(key, p)]
                 rchans[ci]["params"] = self.slab.ptr + self.layout.params_off[(key, p)]
                 rchans[ci]["flag"] = self.slab.ptr + self.layout.flag_off[key] + 4 * p
                 rchans[ci]["ack"] = self.peer_base[p] + self.layouts[p].ack_off[key] + 4 * me
-                rchans[ci]["S"] = ridx.size
-                seg_off = 0
-                prm_off = 0
-                for b in BITS_SET:
-                    ids = np.nonzero(bits_p == b)[0]
-                    if ids.size == 0:
-                        continue
-                    wpt = 8 // b
-                    g = (ids.size + wpt - 1) // wpt
-                    it = np.zeros(g, _lib.RECV_ITEM_DTYPE)
-                    dst = np.full(g * wpt, -1, np.int64)
-                    dst[:ids.size] = ridx[ids]                # remote[recv_idx[p]][orig_ids]
-                    it["dst_row"][:, :wpt] = dst.reshape(g, wpt)
-                    it["dst_row"][:, wpt:] = -1
-                    it["src_off"] = seg_off + np.arange(g, dtype=np.int64) * F
-                    it["param_pos"] = prm_off + np.arange(g, dtype=np.int64) * wpt
-                    it["chan"] = ci
-                    it["bits"] = b
-                    it["nrows"] = np.minimum(wpt, ids.size - np.arange(g) * wpt)
-                    r_items.append(it)
-                    seg_off += qsize(ids.size, b, F)
-                    prm_off += ids.size
-                wire[p] = (seg_off, int(ridx.size))
-            recv_items = np.concatenate(r_items) if r_items else np.zeros(0, _lib.RECV_ITEM_DTYPE)
+                rchans[ci]["S"] = self.recv_idx[p].size
+            recv_items, wire = build_recv_items(self.recv_peers, self.recv_idx,
+                                                {p: np.asarray(metas[p][key][me]) for p in self.recv_peers}, F)
             self.quant_plans[key] = QuantPlan(
                 send_items=_to_device_bytes(send_items, self.device),
                 send_items_compat=_to_device_bytes(compat, self.device), n_send=int(send_items.size),
