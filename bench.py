@@ -257,7 +257,11 @@ def run_ours(args, rank, world):
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
     n_exch = 5 if world > 1 else 0
-    launches_per_epoch = launches + (n_exch * (3 if eng.bit_type.name == "QUANT" else 3))
+    # our kernels per epoch: aggregation launches (the marginal rows take two passes -- local then halo
+    # segment -- unless ADAQP_MARGINAL_SPLIT=0) + per exchange: send, flag wait, receive (quant) or
+    # send, flag wait, ack (fp32)
+    split_extra = 5 if (eng.use_parallel and eng.num_marginal > 0 and os.environ.get("ADAQP_MARGINAL_SPLIT", "1") != "0") else 0
+    launches_per_epoch = launches + split_extra + n_exch * 3
     out = {
         "metric": "epochs_per_sec", "value": args.steps / (ms / 1e3), "unit": "epochs/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
