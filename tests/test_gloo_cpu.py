@@ -21,10 +21,10 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, tmp, mode, model_name, out):
+def _worker(rank, world, port, tmp, mode, model_name, out, dataset="reddit"):
     os.environ.update({"MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port), "RANK": str(rank),
                        "WORLD_SIZE": str(world), "LOCAL_RANK": str(rank), "ADAQP_DEVICE": "cpu",
-                       "ADAQP_SYNTH_SCALE": "0.004", "ADAQP_SEED": "7", "OMP_NUM_THREADS": "1"})
+                       "ADAQP_SYNTH_SCALE": "0.004" if dataset == "reddit" else "0.003", "ADAQP_SEED": "7", "OMP_NUM_THREADS": "1"})
     sys.path.insert(0, ROOT)
     os.chdir(tmp)
     from argparse import Namespace
@@ -32,7 +32,7 @@ def _worker(rank, world, port, tmp, mode, model_name, out):
     from adaqp_b200.communicator import Communicator as comm
     from adaqp_b200.manager import GraphEngine as engine
     from adaqp_b200.model.op_util import msg_all2all_GLOO
-    args = Namespace(dataset="reddit", num_parts=world, backend="gloo", init_method="env://", model_name=model_name,
+    args = Namespace(dataset=dataset, num_parts=world, backend="gloo", init_method="env://", model_name=model_name,
                      mode=mode, assign_scheme="uniform", logger_level="WARNING", num_epoches=3, exp_path=f"{tmp}/exp")
     tr = Trainer(args)
     eng = engine.ctx
@@ -60,13 +60,14 @@ def _worker(rank, world, port, tmp, mode, model_name, out):
     out.put((rank, losses_ok, float(eng.recorder.epoches_metrics[:3, 0].max())))
 
 
-@pytest.mark.parametrize("mode,model_name", [("Vanilla", "gcn"), ("AdaQP-p", "sage")])
-def test_two_rank_cpu_training(mode, model_name):
+@pytest.mark.parametrize("mode,model_name,dataset", [("Vanilla", "gcn", "reddit"), ("AdaQP-p", "sage", "reddit"),
+                                                     ("Vanilla", "sage", "yelp")])
+def test_two_rank_cpu_training(mode, model_name, dataset):
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
     with tempfile.TemporaryDirectory() as tmp:
-        procs = [ctx.Process(target=_worker, args=(r, 2, port, tmp, mode, model_name, out)) for r in range(2)]
+        procs = [ctx.Process(target=_worker, args=(r, 2, port, tmp, mode, model_name, out, dataset)) for r in range(2)]
         for p in procs:
             p.start()
         for p in procs:
@@ -74,4 +75,4 @@ def test_two_rank_cpu_training(mode, model_name):
         assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
         res = sorted(out.get(timeout=5) for _ in procs)
         assert all(ok for _, ok, _ in res)
-        assert os.path.exists(f"{tmp}/exp/reddit/2part/{model_name}/time/{mode}.csv")
+        assert os.path.exists(f"{tmp}/exp/{dataset}/2part/{model_name}/time/{mode}.csv")
