@@ -89,6 +89,17 @@ def _load_config(dataset: str) -> dict:
         return yaml.load(f, Loader=yaml.FullLoader)
 
 
+def save_rank_layout(layout: RankLayout, part_dir: str, dataset: str) -> str:
+    """Write one rank's prepared layout where load_rank_layout looks for it
+    (`<part_dir>/<dataset>/<W>part/part<rank>.npz`): the ingest point for real partitions, e.g. the
+    output of tools/convert_dgl_partition.py run where DGL is installed."""
+    d = f"{part_dir}/{dataset}/{layout.world_size}part"
+    os.makedirs(d, exist_ok=True)
+    path = f"{d}/part{layout.rank}.npz"
+    np.savez_compressed(path, layout=np.array(layout, dtype=object))
+    return path
+
+
 def load_rank_layout(part_dir: str, dataset: str, model_type: DistGNNType) -> RankLayout:
     rank, W = comm.get_rank(), comm.get_world_size()
     path = f"{part_dir}/{dataset}/{W}part/part{rank}.npz"
