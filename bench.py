@@ -231,12 +231,31 @@ def run_ours(args, rank, world):
     # ---- end-to-end: host inputs -> device every step, loss read back
     feats_host = eng.feats.cpu().pin_memory()
     labels_host = eng.labels.cpu().pin_memory()
-    fbuf, lbuf = torch.empty_like(eng.feats), torch.empty_like(eng.labels)
+    # Input pipeline as a user would run it: the pinned-host -> device copy of step i+1 is issued on a
+    # copy stream while step i computes (two device buffers), so every timed step still pays for one
+    # full H2D copy of its inputs and one D2H read of its loss, but the copy hides behind the epoch.
+    copy_stream = torch.cuda.Stream()
+    bufs = [(torch.empty_like(eng.feats), torch.empty_like(eng.labels)) for _ in range(2)]
+    copied = [torch.cuda.Event(), torch.cuda.Event()]
+    e2e_state = {"i": 0}
+
+    def prefetch(i):
+        f, l = bufs[i % 2]
+        copy_stream.wait_stream(torch.cuda.current_stream())   # the buffer's previous reader (step i-2) is done
+        with torch.cuda.stream(copy_stream):
+            f.copy_(feats_host, non_blocking=True)
+            l.copy_(labels_host, non_blocking=True)
+            copied[i % 2].record(copy_stream)
+
+    prefetch(0)
 
     def e2e_step():
-        fbuf.copy_(feats_host, non_blocking=True)
-        lbuf.copy_(labels_host, non_blocking=True)
-        _, loss, _, _ = step(fbuf, lbuf)
+        i = e2e_state["i"]
+        e2e_state["i"] += 1
+        torch.cuda.current_stream().wait_event(copied[i % 2])
+        prefetch(i + 1)
+        f, l = bufs[i % 2]
+        _, loss, _, _ = step(f, l)
         return float(loss.item())
 
     e2e_step()
@@ -276,7 +295,8 @@ def run_ours(args, rank, world):
         "clocks": sampler.summary(),
         "e2e": {"value": args.steps / (ms_e2e / 1e3), "unit": "epochs/s",
                 "h2d_bytes_per_step": int(feats_host.numel() * 4 + labels_host.numel() * labels_host.element_size()),
-                "d2h_bytes_per_step": 4, "api": "train_for_one_epoch(host features -> device, loss.item())"},
+                "d2h_bytes_per_step": 4,
+                "api": "train_for_one_epoch on inputs copied from pinned host memory every step (double-buffered prefetch on a copy stream), loss.item()"},
         "gpu_launches": int(launches_per_epoch * args.steps),
         "roofline": {"kernel": "spmm_csr_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
                      "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_kind": f"of {peak_kind}",
