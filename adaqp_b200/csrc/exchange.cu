@@ -466,6 +466,21 @@ inline int pick_vec(int F, int64_t ld, const void *p0, const void *p1 = nullptr,
     return 1;
 }
 
+// One wave of resident CTAs (persistent-style): ask the runtime how many CTAs of this kernel fit per SM,
+// so that the grid is not the requested cap rounded into a second, partly filled wave.
+template <class K>
+inline int resident_grid(K kernel, size_t smem, int64_t n_items, int cap_ctas_per_sm) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    if (per_sm > cap_ctas_per_sm) per_sm = cap_ctas_per_sm;
+    const int sms = adaqp_sm_count() > 0 ? adaqp_sm_count() : 148;
+    int64_t ctas = (n_items + kWarps - 1) / kWarps;
+    const int64_t cap = (int64_t)sms * per_sm;
+    if (ctas > cap) ctas = cap;
+    if (ctas < 1) ctas = 1;
+    return (int)ctas;
+}
+
 inline int grid_for(int64_t n_items, int max_ctas_per_sm) {
     const int sms = adaqp_sm_count() > 0 ? adaqp_sm_count() : 148;
     int64_t ctas = (n_items + kWarps - 1) / kWarps;
@@ -500,9 +515,8 @@ int adaqp_send_quant(const float *x, int64_t ld, int32_t F, const adaqp_send_ite
     const PhiloxKeys keys = make_philox_keys(seed);
     cudaStream_t s = (cudaStream_t)stream;
 #define CALL_SEND(V, C)                                                                          \
-    send_quant_kernel<V, C><<<grid, kThreads, smem, s>>>(x, ld, F, items, n_items, chans, n_chans, \
-                                                         trace, keys, seed, base_offset, seq, work, \
-                                                         status, timeout_ns)
+    send_quant_kernel<V, C><<<resident_grid(send_quant_kernel<V, C>, smem, n_items, 8), kThreads, smem, s>>>(  \
+        x, ld, F, items, n_items, chans, n_chans, trace, keys, seed, base_offset, seq, work, status, timeout_ns)
     if (vec == 4) {
         if (nchunks <= 1) CALL_SEND(4, 1);
         else if (nchunks <= 2) CALL_SEND(4, 2);
@@ -542,7 +556,7 @@ int adaqp_recv_quant(float *halo, int64_t ld, int32_t F, const adaqp_recv_item *
     const int grid = grid_for(n_items, 8);
     cudaStream_t s = (cudaStream_t)stream;
 #define CALL_RECV(V, C)                                                                          \
-    recv_quant_kernel<V, C><<<grid, kThreads, (size_t)n_chans * sizeof(adaqp_recv_chan), s>>>(halo, ld, F, items, n_items, chans, n_chans, \
+    recv_quant_kernel<V, C><<<resident_grid(recv_quant_kernel<V, C>, (size_t)n_chans * sizeof(adaqp_recv_chan), n_items, 8), kThreads, (size_t)n_chans * sizeof(adaqp_recv_chan), s>>>(halo, ld, F, items, n_items, chans, n_chans, \
                                                       seq, work, status, timeout_ns)
     if (vec == 4) {
         if (nchunks <= 1) CALL_RECV(4, 1);
