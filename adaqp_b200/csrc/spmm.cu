@@ -389,11 +389,16 @@ int adaqp_spmm_csr_seg_f32(const int64_t *indptr, const int64_t *seg_start, cons
     if (ctas_sm < 0) { const char *e = getenv("ADAQP_SPMM_CTAS"); ctas_sm = e ? atoi(e) : 8; if (ctas_sm < 1) ctas_sm = 1; }
     { const int64_t cap2 = (int64_t)sms * ctas_sm; if (grid > cap2) grid = cap2; }
     // per-launch row counter from a small rotating pool (stream-ordered reset)
-    static unsigned long long *pool = nullptr;
-    static unsigned pool_pos = 0;
+    // (one pool per device: a process that drives several devices gets device-local counters)
     constexpr unsigned kPool = 64;
-    if (!pool) ADAQP_CUDA(cudaMalloc(&pool, kPool * sizeof(unsigned long long)));
-    unsigned long long *counter = pool + (pool_pos++ % kPool);
+    constexpr int kMaxDev = 64;
+    static unsigned long long *pools[kMaxDev] = {nullptr};
+    static unsigned pool_pos[kMaxDev] = {0};
+    int dev = 0;
+    ADAQP_CUDA(cudaGetDevice(&dev));
+    ADAQP_REQUIRE(dev >= 0 && dev < kMaxDev, ADAQP_ELIMIT, "adaqp_spmm_csr_seg_f32: device index %d", dev);
+    if (!pools[dev]) ADAQP_CUDA(cudaMalloc(&pools[dev], kPool * sizeof(unsigned long long)));
+    unsigned long long *counter = pools[dev] + (pool_pos[dev]++ % kPool);
     ADAQP_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), s));
 #define CALL_SPMM(V, C)                                                                           \
     spmm_csr_kernel<V, C><<<(unsigned)grid, kThreads, 0, s>>>(indptr, indices, x0, ld0, n_split, x1, \
