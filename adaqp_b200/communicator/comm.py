@@ -68,23 +68,7 @@ class Communicator(object):
                 f"{self.get_world_size()}, local_rank: {self.local_rank}, device: {self.device}, "
                 f"transport: {self.transport})>")
 
-    # ---- getters --------------------------------------------------------------------
-    @property
-    def local_rank(self):
-        return self._local_rank
-
-    @property
-    def device(self):
-        return self._device
-
-    @property
-    def init_method(self):
-        return self._init_method
-
-    @property
-    def backend(self):
-        return self._backend
-
+    # ---- getters (comm.py:46-60): local_rank / device / init_method / backend are attached below ------
     @staticmethod
     def get_rank():
         return dist.get_rank()
@@ -214,3 +198,7 @@ class Communicator(object):
     def delete_buffer(self, *args, **kwargs):
         assert self.comm_buffer is not None, "please initialize the communication buffer first"
         self.comm_buffer._delete(*args, **kwargs)
+
+
+for _public in ("local_rank", "device", "init_method", "backend"):
+    setattr(Communicator, _public, property(lambda self, _f="_" + _public: getattr(self, _f)))

@@ -181,23 +181,7 @@ class GraphEngine(object):
         self.comp_cpu_event = Event()
         self.marginal_pool = None
 
-    # ---- getters (graphEngine.py:169-224) ---------------------------------------------------
-    @property
-    def device(self):
-        return self._device
-
-    @property
-    def is_bidirected(self):
-        return self._is_bidirected
-
-    @property
-    def use_parallel(self):
-        return self._use_parallel
-
-    @property
-    def bit_type(self):
-        return self._bit_type
-
+    # ---- read-only accessors of the reference (graphEngine.py:169-224), generated below ------------------
     @property
     def agg_type(self):
         assert self._agg_type is not None, "please set the aggregator type first."
@@ -207,34 +191,16 @@ class GraphEngine(object):
     def agg_type(self, agg_type: str):
         self._agg_type = agg_type
 
-    @property
-    def num_remove(self):
-        return self._num_remove
 
-    @property
-    def num_inner(self):
-        return self._num_inner
+def _readonly(attr: str):
+    return property(lambda self: getattr(self, attr))
 
-    @property
-    def num_marginal(self):
-        return self._num_marginal
 
-    @property
-    def num_central(self):
-        return self._num_central
-
-    @property
-    def send_idx(self):
-        return self._send_idx
-
-    @property
-    def recv_idx(self):
-        return self._recv_idx
-
-    @property
-    def scores(self):
-        return self._scores
-
-    @property
-    def total_send_idx(self):
-        return self._total_send_idx
+# public name -> private field; `num_remove` is the reference's (historical) spelling of num_remote and is
+# what op_util.py:147 reads, so it is kept verbatim, with `num_remote` as an alias
+for _public, _private in {"device": "_device", "is_bidirected": "_is_bidirected", "use_parallel": "_use_parallel",
+                          "bit_type": "_bit_type", "num_remove": "_num_remove", "num_remote": "_num_remove",
+                          "num_inner": "_num_inner", "num_marginal": "_num_marginal", "num_central": "_num_central",
+                          "send_idx": "_send_idx", "recv_idx": "_recv_idx", "scores": "_scores",
+                          "total_send_idx": "_total_send_idx"}.items():
+    setattr(GraphEngine, _public, _readonly(_private))
