@@ -20,7 +20,7 @@ i32 = C.c_int32
 u64 = C.c_uint64
 u32 = C.c_uint32
 
-ADAQP_ABI_VERSION = 1
+ADAQP_ABI_VERSION = 2
 IPC_HANDLE_BYTES = 64
 ST_OK, ST_FLAG_TIMEOUT, ST_ACK_TIMEOUT = 0, 1, 2
 
@@ -50,6 +50,9 @@ SYMBOLS = {
     "adaqp_abi_version": (C.c_int, []),
     "adaqp_last_error": (C.c_char_p, []),
     "adaqp_sm_count": (C.c_int, []),
+    "adaqp_set_option": (C.c_int, [C.c_char_p, i64]),
+    "adaqp_get_option": (C.c_int, [C.c_char_p, C.POINTER(i64)]),
+    "adaqp_enable_peer_access": (C.c_int, [C.c_int]),
     "adaqp_packed_nbytes": (i64, [i64, i64, C.c_int]),
     "adaqp_qsize": (i64, [i64, i64, C.c_int]),
     "adaqp_pack_f32": (C.c_int, [c_void_p, c_void_p, c_void_p, i64, i64, C.c_int, u64, u64,
@@ -110,7 +113,37 @@ def load():
     if v != ADAQP_ABI_VERSION:
         raise AdaqpLibraryError(f"ABI version mismatch: library {v}, binding {ADAQP_ABI_VERSION}")
     _lib = L
+    _apply_env_options(L)
     return L
+
+
+# environment variable -> library option (read ONCE, here; the library itself never reads the environment)
+ENV_OPTIONS = {"ADAQP_SPMM": "spmm_impl", "ADAQP_SPMM_GRAB": "spmm_rows_per_grab", "ADAQP_SPMM_CTAS": "spmm_ctas_per_sm",
+               "ADAQP_SPMM_HINTS": "spmm_hints", "ADAQP_EXCH_SEND_CTAS": "exch_send_ctas",
+               "ADAQP_EXCH_RECV_CTAS": "exch_recv_ctas"}
+
+
+def _apply_env_options(L):
+    for env, name in ENV_OPTIONS.items():
+        v = os.environ.get(env)
+        if v is not None and v != "":
+            set_option(name, int(v), L)
+
+
+def set_option(name: str, value: int, L=None):
+    L = L or load()
+    rc = L.adaqp_set_option(name.encode(), int(value))
+    if rc != 0:
+        raise ValueError(L.adaqp_last_error().decode("utf-8", "replace"))
+
+
+def get_option(name: str) -> int:
+    L = load()
+    out = i64(0)
+    rc = L.adaqp_get_option(name.encode(), C.byref(out))
+    if rc != 0:
+        raise ValueError(L.adaqp_last_error().decode("utf-8", "replace"))
+    return int(out.value)
 
 
 def check(rc: int, what: str = ""):

@@ -123,7 +123,9 @@ class Assigner(object):
                 combined = (agg ** 2) * traced
                 srt, order = torch.sort(combined, descending=True)
                 g_ids = torch.split(order, group_size)
-                g_var = torch.stack([srt[i:i + group_size].sum() for i in range(0, len(srt), group_size)])
+                # reference expression, kept verbatim for parity (assigner.py:167-171 `group_data`): the SORTED
+                # scores indexed by the group's ORIGINAL row ids, i.e. not the sum of the group's own scores
+                g_var = torch.stack([srt[ids].sum() for ids in g_ids])
                 var_matrix[key][f"{rank}_{pid}"] = (self.bits_cost.view(-1, 1) * g_var.view(1, -1)).numpy()
                 idx_set[key][pid] = g_ids
                 mb = (self.bits_set.view(-1, 1).float() * dim * group_size) / 8 / (1024 ** 2)

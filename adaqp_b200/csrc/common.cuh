@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "../../include/adaqp_b200.h"
 
@@ -12,6 +13,17 @@
 // ---------------------------------------------------------------- errors
 void adaqp_set_error(const char *fmt, ...);
 int adaqp_check_launch(const char *what);
+
+// Tunables set through adaqp_set_option() (runtime.cu); no environment reads in the library.
+struct AdaqpOptions {
+    int spmm_impl;            // 1 register gather (default), 2 cp.async ring, 3 TMA gather4 ring, 4 TMA bulk ring
+    int spmm_rows_per_grab;   // 0 = per-kernel default
+    int spmm_ctas_per_sm;     // frontier kernel grid cap per SM
+    int spmm_hints;           // bit 0: streaming output stores, bit 1: streaming index loads
+    int exch_send_ctas;       // 0 = one resident wave; > 0 = total CTA cap of the send kernels
+    int exch_recv_ctas;       // same for the receive kernel
+};
+AdaqpOptions &adaqp_options();
 
 #define ADAQP_REQUIRE(cond, code, ...)            \
     do {                                          \

@@ -468,14 +468,17 @@ inline int pick_vec(int F, int64_t ld, const void *p0, const void *p1 = nullptr,
 
 // One wave of resident CTAs (persistent-style): ask the runtime how many CTAs of this kernel fit per SM,
 // so that the grid is not the requested cap rounded into a second, partly filled wave.
+// `total_cap` > 0 (options exch_send_ctas / exch_recv_ctas) bounds the grid to a small persistent
+// set of CTAs, so that the SMs left over go to the aggregation the exchange overlaps with.
 template <class K>
-inline int resident_grid(K kernel, size_t smem, int64_t n_items, int cap_ctas_per_sm) {
+inline int resident_grid(K kernel, size_t smem, int64_t n_items, int cap_ctas_per_sm, int total_cap) {
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
     if (per_sm > cap_ctas_per_sm) per_sm = cap_ctas_per_sm;
     const int sms = adaqp_sm_count() > 0 ? adaqp_sm_count() : 148;
     int64_t ctas = (n_items + kWarps - 1) / kWarps;
-    const int64_t cap = (int64_t)sms * per_sm;
+    int64_t cap = (int64_t)sms * per_sm;
+    if (total_cap > 0 && cap > total_cap) cap = total_cap;
     if (ctas > cap) ctas = cap;
     if (ctas < 1) ctas = 1;
     return (int)ctas;
@@ -511,11 +514,10 @@ int adaqp_send_quant(const float *x, int64_t ld, int32_t F, const adaqp_send_ite
     ADAQP_REQUIRE((base_offset & 3u) == 0, ADAQP_EINVAL, "adaqp_send_quant: base_offset must be a multiple of 4 (torch Philox offsets are)");
     ADAQP_REQUIRE(n_chans <= 64, ADAQP_ELIMIT, "adaqp_send_quant: more than 64 channels");
     const size_t smem = (size_t)kWarps * stage_stride + (size_t)n_chans * sizeof(adaqp_send_chan);
-    const int grid = grid_for(n_items, 4);
     const PhiloxKeys keys = make_philox_keys(seed);
     cudaStream_t s = (cudaStream_t)stream;
 #define CALL_SEND(V, C)                                                                          \
-    send_quant_kernel<V, C><<<resident_grid(send_quant_kernel<V, C>, smem, n_items, 8), kThreads, smem, s>>>(  \
+    send_quant_kernel<V, C><<<resident_grid(send_quant_kernel<V, C>, smem, n_items, 8, adaqp_options().exch_send_ctas), kThreads, smem, s>>>(  \
         x, ld, F, items, n_items, chans, n_chans, trace, keys, seed, base_offset, seq, work, status, timeout_ns)
     if (vec == 4) {
         if (nchunks <= 1) CALL_SEND(4, 1);
@@ -553,10 +555,9 @@ int adaqp_recv_quant(float *halo, int64_t ld, int32_t F, const adaqp_recv_item *
     const int vec = pick_vec(F, ld, halo);
     const int nchunks = (F + 32 * vec - 1) / (32 * vec);
     ADAQP_REQUIRE(n_chans <= 64, ADAQP_ELIMIT, "adaqp_recv_quant: more than 64 channels");
-    const int grid = grid_for(n_items, 8);
     cudaStream_t s = (cudaStream_t)stream;
 #define CALL_RECV(V, C)                                                                          \
-    recv_quant_kernel<V, C><<<resident_grid(recv_quant_kernel<V, C>, (size_t)n_chans * sizeof(adaqp_recv_chan), n_items, 8), kThreads, (size_t)n_chans * sizeof(adaqp_recv_chan), s>>>(halo, ld, F, items, n_items, chans, n_chans, \
+    recv_quant_kernel<V, C><<<resident_grid(recv_quant_kernel<V, C>, (size_t)n_chans * sizeof(adaqp_recv_chan), n_items, 8, adaqp_options().exch_recv_ctas), kThreads, (size_t)n_chans * sizeof(adaqp_recv_chan), s>>>(halo, ld, F, items, n_items, chans, n_chans, \
                                                       seq, work, status, timeout_ns)
     if (vec == 4) {
         if (nchunks <= 1) CALL_RECV(4, 1);
@@ -595,7 +596,8 @@ int adaqp_send_fp32(const float *x, int64_t ld, int32_t F, const adaqp_fp_item *
     // destination rows live in slabs allocated 256-byte aligned: alignment follows dst_ld
     int vec = pick_vec(F, ld, x);
     while (vec > 1 && (dst_ld % vec)) vec >>= 1;
-    const int grid = grid_for(n_items, 8);
+    int grid = grid_for(n_items, 8);
+    if (adaqp_options().exch_send_ctas > 0 && grid > adaqp_options().exch_send_ctas) grid = adaqp_options().exch_send_ctas;
     cudaStream_t s = (cudaStream_t)stream;
     if (vec == 4)
         send_fp32_kernel<4><<<grid, kThreads, 0, s>>>(x, ld, F, items, n_items, chans, n_chans, dst_ld, seq, work, status, timeout_ns);

@@ -24,9 +24,56 @@ int adaqp_check_launch(const char *what) {
     return 0;
 }
 
+AdaqpOptions &adaqp_options() {
+    static AdaqpOptions opt = {1, 0, 8, 0, 0, 0};
+    return opt;
+}
+
+namespace {
+int *option_slot(const char *name) {
+    AdaqpOptions &o = adaqp_options();
+    if (!name) return nullptr;
+    if (!strcmp(name, "spmm_impl")) return &o.spmm_impl;
+    if (!strcmp(name, "spmm_rows_per_grab")) return &o.spmm_rows_per_grab;
+    if (!strcmp(name, "spmm_ctas_per_sm")) return &o.spmm_ctas_per_sm;
+    if (!strcmp(name, "spmm_hints")) return &o.spmm_hints;
+    if (!strcmp(name, "exch_send_ctas")) return &o.exch_send_ctas;
+    if (!strcmp(name, "exch_recv_ctas")) return &o.exch_recv_ctas;
+    return nullptr;
+}
+}  // namespace
+
 extern "C" {
 
 int adaqp_abi_version(void) { return ADAQP_ABI_VERSION; }
+
+int adaqp_set_option(const char *name, int64_t value) {
+    int *slot = option_slot(name);
+    ADAQP_REQUIRE(slot != nullptr, ADAQP_EINVAL, "adaqp_set_option: unknown option '%s'", name ? name : "(null)");
+    ADAQP_REQUIRE(value >= 0 && value <= (1 << 20), ADAQP_EINVAL, "adaqp_set_option: %s=%lld out of range", name, (long long)value);
+    *slot = (int)value;
+    return 0;
+}
+
+int adaqp_get_option(const char *name, int64_t *value) {
+    int *slot = option_slot(name);
+    ADAQP_REQUIRE(slot != nullptr && value != nullptr, ADAQP_EINVAL, "adaqp_get_option: unknown option '%s'", name ? name : "(null)");
+    *value = *slot;
+    return 0;
+}
+
+int adaqp_enable_peer_access(int peer_device) {
+    int dev = 0;
+    ADAQP_CUDA(cudaGetDevice(&dev));
+    if (dev == peer_device) return 0;
+    int can = 0;
+    ADAQP_CUDA(cudaDeviceCanAccessPeer(&can, dev, peer_device));
+    ADAQP_REQUIRE(can, ADAQP_EINVAL, "adaqp_enable_peer_access: device %d cannot map device %d", dev, peer_device);
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { (void)cudaGetLastError(); return 0; }
+    ADAQP_CUDA(e);
+    return 0;
+}
 
 const char *adaqp_last_error(void) { return g_err; }
 

@@ -14,6 +14,7 @@ uses one side stream and CUDA events only -- no helper thread, no host synchroni
 from __future__ import annotations
 
 import logging
+import json
 import os
 from multiprocessing import Event
 from typing import List, Tuple
@@ -89,28 +90,61 @@ def _load_config(dataset: str) -> dict:
         return yaml.load(f, Loader=yaml.FullLoader)
 
 
+_ARRAY_FIELDS = ("indptr", "indices", "in_degrees", "out_degrees", "feat", "label", "train_mask", "val_mask",
+                 "test_mask", "total_send_idx", "src_marginal_idx", "src_central_idx")
+_SCALAR_FIELDS = ("rank", "world_size", "n_central", "n_marginal", "n_inner", "n_halo", "is_bidirected")
+
+
 def save_rank_layout(layout: RankLayout, part_dir: str, dataset: str) -> str:
     """Write one rank's prepared layout where load_rank_layout looks for it
     (`<part_dir>/<dataset>/<W>part/part<rank>.npz`): the ingest point for real partitions, e.g. the
-    output of tools/convert_dgl_partition.py run where DGL is installed."""
+    output of tools/convert_dgl_partition.py run where DGL is installed.  Plain ndarrays plus a JSON
+    header only -- nothing in the file is unpickled on load."""
     d = f"{part_dir}/{dataset}/{layout.world_size}part"
     os.makedirs(d, exist_ok=True)
     path = f"{d}/part{layout.rank}.npz"
-    np.savez_compressed(path, layout=np.array(layout, dtype=object))
+    arrays = {k: np.ascontiguousarray(getattr(layout, k)) for k in _ARRAY_FIELDS}
+    header = {k: (bool(getattr(layout, k)) if k == "is_bidirected" else int(getattr(layout, k))) for k in _SCALAR_FIELDS}
+    header["send_idx"] = {str(p): [int(lo), int(hi)] for p, (lo, hi) in layout.send_idx.items()}
+    header["recv_peers"] = [int(p) for p in layout.recv_idx]
+    header["score_peers"] = [int(p) for p in layout.scores]
+    for p, v in layout.recv_idx.items():
+        arrays[f"recv_idx_{int(p)}"] = np.ascontiguousarray(v)
+    for p, (fw, bw) in layout.scores.items():
+        arrays[f"score_fwd_{int(p)}"] = np.ascontiguousarray(fw)
+        arrays[f"score_bwd_{int(p)}"] = np.ascontiguousarray(bw)
+    arrays["header_json"] = np.frombuffer(json.dumps(header).encode("utf-8"), dtype=np.uint8)
+    np.savez_compressed(path, **arrays)
     return path
+
+
+def read_rank_layout(path: str) -> RankLayout:
+    z = np.load(path, allow_pickle=False)
+    h = json.loads(bytes(z["header_json"]).decode("utf-8"))
+    kw = {k: z[k] for k in _ARRAY_FIELDS}
+    kw.update({k: h[k] for k in _SCALAR_FIELDS})
+    kw["send_idx"] = {int(p): (int(v[0]), int(v[1])) for p, v in h["send_idx"].items()}
+    kw["recv_idx"] = {int(p): z[f"recv_idx_{int(p)}"] for p in h["recv_peers"]}
+    kw["scores"] = {int(p): (z[f"score_fwd_{int(p)}"], z[f"score_bwd_{int(p)}"]) for p in h["score_peers"]}
+    return RankLayout(**kw)
 
 
 def load_rank_layout(part_dir: str, dataset: str, model_type: DistGNNType) -> RankLayout:
     rank, W = comm.get_rank(), comm.get_world_size()
     path = f"{part_dir}/{dataset}/{W}part/part{rank}.npz"
     if os.path.exists(path):
-        z = np.load(path, allow_pickle=True)
-        return z["layout"].item()
+        return read_rank_layout(path)
+    # No partition files: the DGL-free synthetic generator is an explicit opt-in, so that a mistyped
+    # partition path cannot silently train on random data under the real dataset's name.
+    if os.environ.get("ADAQP_SYNTHETIC", "0") != "1":
+        raise FileNotFoundError(
+            f"no partition file {path}. Convert real partitions with tools/convert_dgl_partition.py, or set "
+            f"ADAQP_SYNTHETIC=1 to train on synthetic partitions of the dataset's shape (config `synthetic:`).")
     scale = float(os.environ.get("ADAQP_SYNTH_SCALE", "1.0"))
     spec = spec_from_config(_load_config(dataset), W, scale)
     if rank == 0:
-        logger.info(f"<no partition files under {part_dir}/{dataset}/{W}part: synthetic partitions "
-                    f"N={spec.num_nodes} E={spec.num_edges} W={W} seed={spec.seed}>")
+        logger.warning(f"<no partition files under {part_dir}/{dataset}/{W}part: SYNTHETIC partitions "
+                       f"N={spec.num_nodes} E={spec.num_edges} W={W} seed={spec.seed} (ADAQP_SYNTHETIC=1)>")
     return prepare_rank(spec, rank, model_type, comm.gather_all)
 
 

@@ -70,15 +70,18 @@ class PendingExchange(object):
             comm.ctx.comm_buffer.p2p.release_fp(self.key, stream)
 
 
-def _trace_ptr(name: str, n_rows: int, device) -> Optional[Tensor]:
+def _trace_ptr(name: str, n_rows: int, device, stream=None) -> Optional[Tensor]:
     """trace_input (op_util.py:91-99) fused into the send kernel: the per-row
-    (dim / 6) * (max - min)^2 accumulates into Assigner.traced_layer_data[name]."""
+    (dim / 6) * (max - min)^2 accumulates into Assigner.traced_layer_data[name].
+    The accumulator is allocated AND zero-filled on the stream the send kernel runs on, so the
+    fill is ordered before the kernel's read-modify-write (the side stream in overlap modes)."""
     a = assigner.ctx
     if a is None or not a.is_tracing:
         return None
     cur = a.traced_layer_data.get(name)
     if not isinstance(cur, Tensor):
-        cur = torch.zeros(n_rows, dtype=torch.float32, device=device)
+        with torch.cuda.stream(stream if stream is not None else torch.cuda.current_stream(device)):
+            cur = torch.zeros(n_rows, dtype=torch.float32, device=device)
         a.traced_layer_data[name] = cur
     return cur
 
@@ -100,7 +103,7 @@ def halo_exchange(messages: Tensor, name: str, is_train: bool, gathered: bool = 
     # one philox_engine_inputs(F * 8/bits) per (peer, bit) pack call of the reference
     torch.cuda.default_generators[messages.device.index].set_offset(offset + plan.philox_increment)
     n_send = int(engine.ctx.total_send_idx.numel())
-    ex.post_send_quant(key, messages, seed, offset, trace=_trace_ptr(name, n_send, messages.device),
+    ex.post_send_quant(key, messages, seed, offset, trace=_trace_ptr(name, n_send, messages.device, stream),
                        gathered=gathered, stream=stream)
     ex.wait_flags_quant(key, stream=stream)
     halo = ex.complete_recv_quant(key, stream=stream)

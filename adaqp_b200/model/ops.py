@@ -103,14 +103,21 @@ def _eval_layer0(class_name: str, ctx, local_messages: Tensor, graph, layer: int
               and not (assigner.ctx is not None and assigner.ctx.is_tracing))
     if not usable:
         return fn(ctx, local_messages, graph, layer, is_train, ProprogationMode.Forward, class_name)
-    key = (class_name, local_messages.data_ptr(), local_messages._version, tuple(local_messages.shape))
+    # keyed on the tensor OBJECT (held alive by the cache, so its address cannot be recycled), its version
+    # counter, the graph and the aggregator; only the engine's own constant feature matrix is cached, so
+    # every rank takes the same branch (a hit skips the exchange: ranks must agree or the key's sequence
+    # numbers would diverge)
+    if local_messages is not eng.feats:
+        return fn(ctx, local_messages, graph, layer, is_train, ProprogationMode.Forward, class_name)
+    key = (class_name, local_messages._version, tuple(local_messages.shape), id(graph),
+           eng._agg_type if class_name == "DistAggSAGE" else None)
     cache = getattr(eng, "_eval_layer0_cache", None)
-    if cache is None or cache[0] != key:
+    if cache is None or cache[0] is not local_messages or cache[1] != key:
         out = fn(ctx, local_messages, graph, layer, is_train, ProprogationMode.Forward, class_name)
-        eng._eval_layer0_cache = (key, out)
+        eng._eval_layer0_cache = (local_messages, key, out)
         return out
     ctx.saved = layer
-    return cache[1]
+    return cache[2]
 
 
 class DistAggConv(Function):

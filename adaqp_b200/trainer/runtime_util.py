@@ -97,6 +97,15 @@ def average_gradients(model: nn.Module):
         g.copy_(r)
 
 
+def _check_exchange_status():
+    """A flag / ack spin that timed out inside the exchange kernels only sets the slab's status word (the
+    kernels cannot raise): poll it once per epoch / evaluation, after the step's synchronisation point, and
+    turn it into an exception instead of training on stale halo rows."""
+    buf = comm.ctx.comm_buffer
+    if buf is not None and getattr(buf, "p2p", None) is not None:
+        buf.p2p.check_status()
+
+
 def train_for_one_epoch(epoch: int, graph, model: nn.Module, input_data: Tensor, labels: Tensor,
                         optimizer: Optimizer, criterion: Union[nn.Module, Any], total_num_training_samples: int,
                         train_mask: Tensor) -> Tuple[Any, Tensor, List[float], float]:
@@ -120,6 +129,7 @@ def train_for_one_epoch(epoch: int, graph, model: nn.Module, input_data: Tensor,
     if comm.ctx.device.type == "cuda":
         torch.cuda.synchronize()
     epoch_time = time.time() - epoch_start
+    _check_exchange_status()
     engine.ctx.last_exposed_comm_ms = engine.ctx.timer.exposed_comm_ms()
     traced_time = engine.ctx.timer.epoch_traced_time()
     engine.ctx.timer.clear()
@@ -136,6 +146,7 @@ def val_test(graph, model: nn.Module, input_data: Tensor, labels: Tensor, train_
     for mask in (train_mask, val_mask, test_mask):
         metrics.extend(get_metrics(labels[mask], logits[mask], is_multilabel))
     engine.ctx.timer.clear(is_train=False)
+    _check_exchange_status()
     return metrics
 
 

@@ -40,7 +40,19 @@ def parse():
     p.add_argument("--assign_scheme", type=str, default="random")
     p.add_argument("--scale", type=float, default=float(os.environ.get("ADAQP_SYNTH_SCALE", "1.0")))
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-verify", action="store_true",
+                   help="skip the parity_check leg (cross-GPU exchange vs the CPU oracle, one training step vs the "
+                        "reference flow); it runs OUTSIDE the timed region")
+    p.add_argument("--verify-window", type=int, default=64, help="byte-rows per compared window (<=0: everything)")
     return p.parse_args()
+
+
+def workload_config(args, cfg, world, dims):
+    """`config` of the JSON line -- built by ONE function for both arms so the dicts are identical."""
+    return {"workload": f"{args.dataset}-shape {args.model_name} 3x256 full-graph training epoch, {world} partition(s), "
+                        f"mode {args.mode}, bits {args.assign_scheme}{{2,4,8}}",
+            "nodes": int(cfg["synthetic"]["num_nodes"] * args.scale), "edges": int(cfg["synthetic"]["num_edges"] * args.scale),
+            "layer_dims": dims, "parallelism": f"graph-partition x{world}", "l2": "inputs >> L2 (no flush needed)"}
 
 
 def setup_env(args):
@@ -50,6 +62,7 @@ def setup_env(args):
     os.environ.setdefault("WORLD_SIZE", "1")
     os.environ.setdefault("LOCAL_RANK", "0")
     os.environ["ADAQP_SYNTH_SCALE"] = str(args.scale)
+    os.environ.setdefault("ADAQP_SYNTHETIC", "1")      # datasets / DGL partitions are not in the image: synthetic shape
     os.environ.setdefault("ADAQP_SEED", "2024")
     world = int(os.environ["WORLD_SIZE"])
     if world != args.gpus:
@@ -286,12 +299,9 @@ def run_ours(args, rank, world):
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "exposed_comm_ms": float(gl[2].item()),
-        "config": {"workload": f"{args.dataset}-shape {args.model_name} 3x256 full-graph training epoch, {world} partition(s), "
-                               f"mode {args.mode}, bits {args.assign_scheme}{{2,4,8}}",
-                   "nodes": int(cfg["synthetic"]["num_nodes"] * args.scale), "edges": int(cfg["synthetic"]["num_edges"] * args.scale),
-                   "layer_dims": dims, "parallelism": f"graph-partition x{world}", "l2": "inputs >> L2 (no flush needed)",
-                   "rank0": {"n_inner": eng.num_inner, "n_central": eng.num_central, "n_halo": eng.num_remove,
-                             "nnz": int(eng.layout.indptr[-1])}},
+        "config": workload_config(args, cfg, world, dims),
+        "rank0": {"n_inner": eng.num_inner, "n_central": eng.num_central, "n_halo": eng.num_remove,
+                  "nnz": int(eng.layout.indptr[-1])},
         "clocks": sampler.summary(),
         "e2e": {"value": args.steps / (ms_e2e / 1e3), "unit": "epochs/s",
                 "h2d_bytes_per_step": int(feats_host.numel() * 4 + labels_host.numel() * labels_host.element_size()),
@@ -308,14 +318,24 @@ def run_ours(args, rank, world):
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_port(eng, dims)
+    if not args.no_verify:
+        # outside the timed region: what the peers wrote into my slab over NVLink vs the CPU oracle
+        # (bit-exact), and one training step vs the reference flow around the reference's own kernels
+        from tools import parity_check
+        out["parity_check"] = parity_check.parity_check(tr, window_groups=args.verify_window)
     comm.ctx.delete_buffer()
     if rank == 0:
         print(json.dumps(out), flush=True)
 
 
 def run_reference(args, rank, world):
+    import yaml
     from oracle import ref_path
+    cfg = yaml.safe_load(open(os.path.join(ROOT, "adaqp_b200", "config", f"{args.dataset}.yaml")))
+    dims = [cfg["data"]["num_feats"]] + [cfg["model"]["hidden_dim"]] * (cfg["model"]["num_layers"] - 1)
     out = ref_path.bench(args, rank, world)
+    if "config" in out:
+        out["config"] = workload_config(args, cfg, world, dims)
     if rank == 0:
         print(json.dumps(out), flush=True)
 

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define ADAQP_ABI_VERSION 1
+#define ADAQP_ABI_VERSION 2
 
 #define ADAQP_EINVAL (-1)   /* bad argument (bits not in {1,2,4,8}, negative size ...) */
 #define ADAQP_EALIGN (-2)   /* pointer alignment requirement violated */
@@ -43,6 +43,15 @@ int adaqp_abi_version(void);
 const char *adaqp_last_error(void);
 /* number of SMs of the current device (grid sizing); <0 on error */
 int adaqp_sm_count(void);
+/* Process-wide tunables (the library never reads the environment; adaqp_b200/_lib.py maps ADAQP_*
+ * variables onto these once at load).  Names: "spmm_impl" (1 register gather [default], 2 cp.async
+ * ring, 3 TMA tile::gather4 ring, 4 TMA bulk-per-row ring), "spmm_rows_per_grab" (0 = default),
+ * "spmm_ctas_per_sm", "spmm_hints" (bit 0 streaming output stores, bit 1 streaming index loads),
+ * "exch_send_ctas" / "exch_recv_ctas" (0 = one resident wave over all SMs, n = at most n CTAs, so
+ * that the exchange kernels leave the remaining SMs to the overlapped aggregation,
+ * SURVEY.md 7 step 7 -- the reference instead serialises them, ops.py:119-130). */
+int adaqp_set_option(const char *name, int64_t value);
+int adaqp_get_option(const char *name, int64_t *value);
 
 /* ------------------------------------------------------------ single codec
  * Replaces quant_cuda.pack_single_precision / unpack_single_precision
@@ -87,6 +96,10 @@ int adaqp_ipc_open(const unsigned char handle[ADAQP_IPC_HANDLE_BYTES], void **pt
 int adaqp_ipc_close(void *ptr);
 /* 1 if the current device can map `peer_device` memory */
 int adaqp_can_access_peer(int peer_device);
+/* cudaDeviceEnablePeerAccess(peer_device) for the current device (idempotent): lets ONE process
+ * that drives several GPUs address their slabs directly (tools/bench_exchange.py --devices, the
+ * single-process harness ncu can profile; multi-process runs map slabs with the IPC calls above). */
+int adaqp_enable_peer_access(int peer_device);
 
 /* --------------------------------------------------------- fused exchange
  * One channel = (this rank, one peer) for one layer key.

@@ -48,6 +48,8 @@ def lib():
         L.oracle_curand_uniform.restype = C.c_float
         L.oracle_pack.argtypes = [f32p, f32p, f32p, C.c_int64, C.c_int64, C.c_int,
                                   C.c_uint64, C.c_uint64, u8p]
+        L.oracle_pack_at.argtypes = [f32p, f32p, f32p, C.c_int64, C.c_int64, C.c_int,
+                                     C.c_uint64, C.c_uint64, C.c_int64, u8p]
         L.oracle_unpack.argtypes = [u8p, f32p, f32p, C.c_int64, C.c_int64, C.c_int, f32p]
         L.oracle_minmax_scale.argtypes = [f32p, C.c_int64, C.c_int64, C.c_int, f32p, f32p, f32p]
         L.oracle_f32_to_bf16_n.argtypes = [f32p, C.c_int64, u16p]
@@ -113,6 +115,20 @@ def pack(data, mn, scale, bits: int, seed: int, offset: int) -> np.ndarray:
     out = np.zeros(packed_nbytes(N, F, bits), dtype=np.uint8)
     lib().oracle_pack(_p(data, C.c_float), _p(mn, C.c_float), _p(scale, C.c_float),
                       N, F, bits, seed, offset, _p(out, C.c_uint8))
+    return out
+
+
+def pack_at(data, mn, scale, bits: int, seed: int, offset: int, group0: int) -> np.ndarray:
+    """Bytes [group0*F, group0*F + ceil(N/wpt)*F) of a pack call whose rows
+    [group0*wpt, group0*wpt + N) are `data` (same Philox subsequences as the full call)."""
+    data = _f32(data)
+    N, F = data.shape
+    mn = _f32(mn)
+    scale = _f32(scale)
+    out = np.zeros(packed_nbytes(N, F, bits), dtype=np.uint8)
+    if N:
+        lib().oracle_pack_at(_p(data, C.c_float), _p(mn, C.c_float), _p(scale, C.c_float),
+                             N, F, bits, seed, offset, group0, _p(out, C.c_uint8))
     return out
 
 

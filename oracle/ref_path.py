@@ -79,13 +79,16 @@ class RefTimer:
 class RefState:
     """Per-rank state of the reference's GraphEngine + CommBuffer (restated)."""
 
-    def __init__(self, layout, device, dims, quant: bool, parallel: bool, qc):
+    def __init__(self, layout, device, dims, quant: bool, parallel: bool, qc, kind: str = "gcn"):
         L = layout
         self.L, self.dev, self.dims, self.quant, self.parallel, self.qc = L, device, dims, quant, parallel, qc
+        self.kind = kind                                          # 'gcn' | 'sage' (mean aggregator)
         self.rank, self.W = L.rank, L.world_size
         ind = torch.from_numpy(L.in_degrees).float().clamp(min=1).to(device)
         outd = torch.from_numpy(L.out_degrees).float().clamp(min=1).to(device)
-        self.norm = {"in": ind.pow(-0.5), "out": outd.pow(-0.5)}
+        self.norm = {"in": ind.pow(-0.5), "out": outd.pow(-0.5), "out_-1": torch.pow(outd, -1)}
+        # DGL fn.mean divides by the number of messages = in-degree inside the partition graph
+        self.local_indeg = torch.from_numpy(np.diff(L.indptr).astype(np.float32)).to(device)
         n_all = L.n_inner + L.n_halo
 
         def csr(lo, hi):
@@ -243,18 +246,31 @@ class RefState:
             h = torch.cat([h, h.new_zeros(csr.shape[1] - h.shape[0], h.shape[1])], 0)
         return torch.sparse.mm(csr, h) * n2[lo:hi].view(-1, 1)
 
+    # ---- ops.py:34-67, aggregator_type='mean' -------------------------------------------------------------
+    def sage_agg(self, csr, feats, lo, hi, backward):
+        h = feats * self.norm["out_-1"][:feats.shape[0]].view(-1, 1) if backward else feats
+        if h.shape[0] < csr.shape[1]:
+            h = torch.cat([h, h.new_zeros(csr.shape[1] - h.shape[0], h.shape[1])], 0)
+        out = torch.sparse.mm(csr, h)
+        if not backward:
+            out = out / self.local_indeg[lo:hi].clamp(min=1).view(-1, 1)
+        return out
+
+    def agg(self, csr, feats, lo, hi, backward):
+        return (self.gcn_agg if self.kind == "gcn" else self.sage_agg)(csr, feats, lo, hi, backward)
+
     def propagate(self, x, layer, is_train, backward):
         name = f"backward{layer}" if backward else f"forward{layer}"
         L = self.L
         if self.W == 1:
             with self.timer.record(f"{name}_full_aggregation"):
-                return self.gcn_agg(self.full, x, 0, L.n_inner, backward)
+                return self.agg(self.full, x, 0, L.n_inner, backward)
         if not self.parallel:                                  # ops.py:132-154
             send = x[self.total_send_idx]
             remote = self.all2all(send, name, is_train)
             full = torch.cat([x, remote], dim=0)
             with self.timer.record(f"{name}_full_aggregation"):
-                return self.gcn_agg(self.full, full, 0, L.n_inner, backward)
+                return self.agg(self.full, full, 0, L.n_inner, backward)
         torch.cuda.current_stream().synchronize()               # ops.py:162
         send = x[self.total_send_idx]
         resp = self.pool.apply_async(self.all2all, args=(send, name, is_train))
@@ -263,7 +279,7 @@ class RefState:
             self.quant_cpu.wait()
             torch.cuda.current_stream().wait_event(self.quant_ev)
         with self.timer.record(f"{name}_central_aggregation"):
-            cen = self.gcn_agg(self.central, x, 0, L.n_central, backward)
+            cen = self.agg(self.central, x, 0, L.n_central, backward)
         if q:
             self.comp_ev.record(torch.cuda.current_stream())
             self.comp_cpu.set()                                 # never cleared, as in the reference
@@ -273,7 +289,7 @@ class RefState:
         self.timer.rec[f"{name}_exposed"] = self.timer.rec.get(f"{name}_exposed", 0.0) + time.time() - t0
         full = torch.cat([x, remote], dim=0)
         with self.timer.record(f"{name}_marginal_aggregation"):
-            mar = self.gcn_agg(self.marginal, full, L.n_central, L.n_inner, backward)
+            mar = self.agg(self.marginal, full, L.n_central, L.n_inner, backward)
         return torch.cat([cen, mar], dim=0)
 
 
@@ -316,6 +332,54 @@ class RefGCN(nn.Module):
         return x
 
 
+class RefSAGE(nn.Module):
+    """distSAGE.py:14-97, aggregator 'mean': fc_self(h) + fc_neigh(mean of in-neighbours) + bias."""
+
+    def __init__(self, dims, classes, drop):
+        super().__init__()
+        sizes = dims + [classes]
+        gain = nn.init.calculate_gain("relu")
+        n = len(dims)
+        self.fc_self = nn.ModuleList([nn.Linear(sizes[i], sizes[i + 1], bias=False) for i in range(n)])
+        self.fc_neigh = nn.ModuleList([nn.Linear(sizes[i], sizes[i + 1], bias=False) for i in range(n)])
+        for m in list(self.fc_self) + list(self.fc_neigh):
+            nn.init.xavier_uniform_(m.weight, gain=gain)
+        self.b = nn.ParameterList([nn.Parameter(torch.zeros(sizes[i + 1])) for i in range(n)])
+        self.norms = nn.ModuleList([nn.LayerNorm(sizes[i + 1]) for i in range(n - 1)])
+        self.drop = drop
+
+    def forward(self, state, x):
+        n = len(self.b)
+        for i in range(n):
+            h = _RefAgg.apply(x, state, i, self.training)
+            x = self.fc_self[i](x) + self.fc_neigh[i](h) + self.b[i]
+            if i < n - 1:
+                x = F.relu(self.norms[i](F.dropout(x, p=self.drop, training=self.training)))
+        return x
+
+
+def make_model(kind: str, dims, classes, drop):
+    return RefGCN(dims, classes, drop) if kind == "gcn" else RefSAGE(dims, classes, drop)
+
+
+def load_product_state(ref: nn.Module, state: Dict[str, torch.Tensor]):
+    """Copy a product DistGCN / DistSAGE state_dict (reference parameter names, distGCN.py:52-75,
+    distSAGE.py:62-80) into the restated model, for the same-weights activation cross-check."""
+    with torch.no_grad():
+        if isinstance(ref, RefGCN):
+            for i in range(len(ref.w)):
+                ref.w[i].copy_(state[f"convs.{i}.weight"])
+                ref.b[i].copy_(state[f"convs.{i}.bias"])
+        else:
+            for i in range(len(ref.b)):
+                ref.fc_self[i].weight.copy_(state[f"sages.{i}.fc_self.weight"])
+                ref.fc_neigh[i].weight.copy_(state[f"sages.{i}.fc_neigh.weight"])
+                ref.b[i].copy_(state[f"sages.{i}.bias"])
+        for i in range(len(ref.norms)):
+            ref.norms[i].weight.copy_(state[f"norms.{i}.weight"])
+            ref.norms[i].bias.copy_(state[f"norms.{i}.bias"])
+
+
 def bench(args, rank, world):
     """K training epochs of the reference flow; same JSON contract as the product arm."""
     import yaml
@@ -345,9 +409,10 @@ def bench(args, rank, world):
         dist.all_gather_object(out, obj)
         return out
 
-    L = prepare_rank(spec, rank, DistGNNType.DistGCN, gather)
+    kind = args.model_name
+    L = prepare_rank(spec, rank, DistGNNType.DistGCN if kind == "gcn" else DistGNNType.DistSAGE, gather)
     dims = [cfg["data"]["num_feats"]] + [cfg["model"]["hidden_dim"]] * (cfg["model"]["num_layers"] - 1)
-    st = RefState(L, dev, dims, quant, parallel, qc)
+    st = RefState(L, dev, dims, quant, parallel, qc, kind)
     torch.manual_seed(2024)
     torch.cuda.manual_seed(2024)
     if quant and world > 1:
@@ -357,7 +422,7 @@ def bench(args, rank, world):
                           else torch.full((hi - lo,), cfg["assignment"]["assign_bits"], dtype=torch.int32))
                       for p, (lo, hi) in L.send_idx.items()} for k in keys}
         st.update_quant(assign)
-    model = RefGCN(dims, cfg["data"]["num_classes"], cfg["model"]["dropout_rate"]).to(dev)
+    model = make_model(kind, dims, cfg["data"]["num_classes"], cfg["model"]["dropout_rate"]).to(dev)
     for v in model.state_dict().values():
         if rank != 0:
             v.zero_()
@@ -368,7 +433,7 @@ def bench(args, rank, world):
     n_train = torch.LongTensor([train_mask.numel()])
     dist.all_reduce(n_train)
     opt = torch.optim.Adam(model.parameters(), lr=cfg["runtime"]["learning_rate"])
-    crit = nn.CrossEntropyLoss(reduction="sum")
+    crit = nn.BCEWithLogitsLoss(reduction="sum") if cfg["data"]["is_multilabel"] else nn.CrossEntropyLoss(reduction="sum")
 
     def epoch():
         model.train()

@@ -24,7 +24,7 @@ def _free_port():
 
 def _worker(rank, world, port, tmp, out):
     os.environ.update({"MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port), "RANK": str(rank), "WORLD_SIZE": str(world),
-                       "LOCAL_RANK": str(rank), "ADAQP_DEVICE": "cpu", "ADAQP_SYNTH_SCALE": "0.002", "OMP_NUM_THREADS": "1"})
+                       "LOCAL_RANK": str(rank), "ADAQP_DEVICE": "cpu", "ADAQP_SYNTH_SCALE": "0.002", "OMP_NUM_THREADS": "1", "ADAQP_SYNTHETIC": "1"})
     sys.path.insert(0, ROOT)
     os.chdir(tmp)
     from adaqp_b200.assigner import Assigner

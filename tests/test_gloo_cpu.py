@@ -24,7 +24,7 @@ def _free_port():
 def _worker(rank, world, port, tmp, mode, model_name, out, dataset="reddit"):
     os.environ.update({"MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port), "RANK": str(rank),
                        "WORLD_SIZE": str(world), "LOCAL_RANK": str(rank), "ADAQP_DEVICE": "cpu",
-                       "ADAQP_SYNTH_SCALE": "0.004" if dataset == "reddit" else "0.003", "ADAQP_SEED": "7", "OMP_NUM_THREADS": "1"})
+                       "ADAQP_SYNTH_SCALE": "0.004" if dataset == "reddit" else "0.003", "ADAQP_SEED": "7", "OMP_NUM_THREADS": "1", "ADAQP_SYNTHETIC": "1"})
     sys.path.insert(0, ROOT)
     os.chdir(tmp)
     from argparse import Namespace

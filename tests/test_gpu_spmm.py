@@ -21,6 +21,20 @@ def build(W, n, deg, F, seed=0):
     return prepare_all_in_process(spec)
 
 
+@pytest.fixture(params=[1, 3, 4], ids=["v1-register-gather", "v3-tma-gather4", "v4-tma-bulk"])
+def impl(request):
+    """The aggregation variants behind option spmm_impl: v1 is the default; v3 (TMA tile::gather4 ring)
+    and v4 (one TMA bulk copy per row) are opt-in and fall back to v1 where their 16-byte / one-box
+    constraints do not hold (F = 602, 13, 300, 1)."""
+    from adaqp_b200 import build as b
+    b.build()
+    from adaqp_b200 import _lib
+    old = _lib.get_option("spmm_impl")
+    _lib.set_option("spmm_impl", request.param)
+    yield request.param
+    _lib.set_option("spmm_impl", old)
+
+
 def check(got, want, x_abs_rowsum_bound):
     err = np.abs(got.astype(np.float64) - want)
     tol = 2e-5 * x_abs_rowsum_bound[:, None] + 1e-6
@@ -29,7 +43,7 @@ def check(got, want, x_abs_rowsum_bound):
 
 @pytest.mark.parametrize("F", [256, 100, 602, 13, 300, 200, 1])
 @pytest.mark.parametrize("W", [1, 3])
-def test_gcn_and_sage_aggregation(F, W):
+def test_gcn_and_sage_aggregation(F, W, impl):
     from adaqp_b200.manager.graph import LocalGraph, spmm
     dev = torch.device("cuda:0")
     lays = build(W, 1500, 14, F, seed=F)
@@ -57,6 +71,32 @@ def test_gcn_and_sage_aggregation(F, W):
     cen = spmm(g, xl, None, g.norm["out_-0.5"], g.norm["in_-0.5"], row_begin=0, row_end=L.n_central)
     mar = spmm(g, xl, xh, g.norm["out_-0.5"], g.norm["in_-0.5"], row_begin=L.n_central, row_end=L.n_inner)
     assert torch.equal(torch.cat([cen, mar]), full)
+    # the self-resetting row counter: back-to-back launches on two streams give the same rows
+    s2 = torch.cuda.Stream()
+    s2.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s2):
+        again = spmm(g, xl, xh, g.norm["out_-0.5"], g.norm["in_-0.5"])
+    again2 = spmm(g, xl, xh, g.norm["out_-0.5"], g.norm["in_-0.5"])
+    torch.cuda.synchronize()
+    assert torch.equal(again, full) and torch.equal(again2, full)
+
+
+@pytest.mark.parametrize("hints", [1, 2, 3])
+def test_streaming_hints_do_not_change_results(hints):
+    from adaqp_b200 import _lib
+    from adaqp_b200.manager.graph import LocalGraph, spmm
+    dev = torch.device("cuda:0")
+    L = build(2, 1200, 12, 256, seed=4)[0]
+    g = LocalGraph(L.indptr, L.indices, L.in_degrees, L.out_degrees, L.n_inner, L.n_halo, dev)
+    xl = torch.randn(L.n_inner, 256, device=dev)
+    xh = torch.randn(L.n_halo, 256, device=dev)
+    base = spmm(g, xl, xh, g.norm["out_-0.5"], g.norm["in_-0.5"])
+    _lib.set_option("spmm_hints", hints)
+    try:
+        got = spmm(g, xl, xh, g.norm["out_-0.5"], g.norm["in_-0.5"])
+    finally:
+        _lib.set_option("spmm_hints", 0)
+    assert torch.equal(got, base)
 
 
 def test_strided_and_unaligned_inputs():
@@ -75,7 +115,7 @@ def test_strided_and_unaligned_inputs():
 
 
 @pytest.mark.parametrize("F,kind", [(256, "gcn"), (100, "sage_mean"), (13, "sage_gcn")])
-def test_local_plus_halo_segments_equal_full_row(F, kind):
+def test_local_plus_halo_segments_equal_full_row(F, kind, impl):
     """Splitting each marginal row into its local-source and halo-source segments (overlap of the
     local part with the exchange) reproduces the single-pass result to fp32 rounding."""
     from adaqp_b200.manager.graph import LocalGraph, spmm
@@ -95,6 +135,12 @@ def test_local_plus_halo_segments_equal_full_row(F, kind):
     spmm(g, xl, xh, row_begin=lo, row_end=hi, out=two, part="halo", **kw)
     scale = full.abs().max().item()
     assert (two - full).abs().max().item() <= 4e-6 * scale
+    if impl != 1:       # same rows from the default kernel (summation order differs only across 4-row groups)
+        from adaqp_b200 import _lib
+        _lib.set_option("spmm_impl", 1)
+        ref = spmm(g, xl, xh, row_begin=lo, row_end=hi, **kw)
+        _lib.set_option("spmm_impl", impl)
+        assert (ref - full).abs().max().item() <= 4e-6 * scale
     # the halo split really separates the sources
     split = g.halo_split.cpu().numpy()
     for r in range(lo, min(lo + 50, hi)):

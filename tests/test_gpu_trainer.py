@@ -64,7 +64,7 @@ def _oracle_forward(layouts, state, model_name, agg_type="mean"):
 def _worker(rank, world, port, tmp, mode, model_name, scheme, ngpu, out):
     os.environ.update({"MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port), "RANK": str(rank),
                        "WORLD_SIZE": str(world), "LOCAL_RANK": str(rank % ngpu),
-                       "ADAQP_SYNTH_SCALE": "0.004", "ADAQP_SEED": "11"})
+                       "ADAQP_SYNTH_SCALE": "0.004", "ADAQP_SEED": "11", "ADAQP_SYNTHETIC": "1"})
     sys.path.insert(0, ROOT)
     os.chdir(tmp)
     from argparse import Namespace

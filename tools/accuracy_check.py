@@ -50,6 +50,7 @@ def main():
     ap.add_argument("--feature-signal", dest="signal", type=float, default=0.12, help="class-centroid strength of the synthetic features")
     args = ap.parse_args()
     os.environ["ADAQP_SYNTH_SCALE"] = str(args.scale)
+    os.environ.setdefault("ADAQP_SYNTHETIC", "1")
     os.environ["ADAQP_SYNTH_SIGNAL"] = str(args.signal)
     os.environ.setdefault("ADAQP_SEED", "123")
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
