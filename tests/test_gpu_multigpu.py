@@ -11,8 +11,10 @@ Checked, all bit-for-bit (integer path) unless a tolerance is stated:
   * dequantised halo rows == oracle unpack (op_util.py:211-236); fp32 exchange rows;
   * forward0 halo of the product == halo of the reference flow around the REFERENCE's own
     quant_cuda kernels (oracle/_ref), same generator seed;
-  * one training step, product vs reference flow: final-layer activations and first-layer
-    weight gradient within parity_check.ACT_TOL (relative to the largest magnitude);
+  * one training step, product vs the reference flow (sequential form; its helper-thread overlap
+    reads send_messages across streams without an event and is not deterministic): final-layer
+    activations and first-layer weight gradient within parity_check.ACT_TOL (max, relative to the
+    largest magnitude), ACT_MEAN_TOL (mean) and LOSS_TOL;
   * the flattened NCCL all-reduce of the gradients == per-parameter gloo
     all-reduce (runtime_util.py:71-77) -- bit-exact at W=2 (one fp32 add per element,
     commutative), <= 1e-6 relative otherwise (reduction order).
@@ -59,6 +61,8 @@ def _worker(rank, world, port, tmp, mode, model_name, scheme, dataset, ngpu, out
     ru.sync_model(tr.model)
     res = parity_check.exchange_parity(window_groups=0)
     res["activations"] = parity_check.activation_parity(tr)
+    if os.environ.get("ADAQP_TEST_OVERLAPPED_REF") == "1":
+        res["activations_overlapped_ref"] = parity_check.activation_parity(tr, overlapped=True)
     # 8f-1: bucketed NCCL reduction vs the reference's per-parameter gloo reduction
     res["nccl"] = None
     grp = ru._reduce_group()
@@ -94,26 +98,29 @@ def _run(world, ngpu, mode, model_name, scheme, dataset="ogbn-products"):
 
 
 def _check(res, world, quant=True):
-    from tools.parity_check import ACT_TOL
+    from tools.parity_check import ACT_MEAN_TOL, ACT_TOL, LOSS_TOL
     assert res["mismatches"] == 0, res
     assert res["fp32_values_compared"] > 0
     if quant:
         assert res["bytes_compared"] > 0 and res["halo_values_compared"] > 0 and res["params_compared"] > 0
     act = res["activations"]
+    print("PARITY", {k: v for k, v in res.items() if not k.startswith("activations")}, act, res.get("activations_overlapped_ref"))
     assert "error" not in act and "unavailable" not in act, act
     if quant:
         assert act["forward0_halo_vs_reference_kernels"]["mismatches"] == 0, act
-    assert act["act_max_rel_err"] <= ACT_TOL, act
-    assert act["grad0_max_rel_err"] <= 5 * ACT_TOL, act
+    assert act["act_max_rel_err"] <= ACT_TOL and act["act_mean_rel_err"] <= ACT_MEAN_TOL, act
+    assert act["grad0_max_rel_err"] <= ACT_TOL and act["loss_rel_diff"] <= LOSS_TOL, act
 
 
 @pytest.mark.parametrize("mode,model_name,scheme,dataset", [
     ("AdaQP", "gcn", "random", "ogbn-products"), ("AdaQP-q", "sage", "random", "ogbn-products"),
-    ("AdaQP", "gcn", "uniform", "reddit"), ("Vanilla", "gcn", "uniform", "ogbn-products")])
+    ("AdaQP", "gcn", "uniform", "reddit"), ("Vanilla", "gcn", "uniform", "ogbn-products"),
+    ("AdaQP", "gcn", "uniform", "ogbn-products"), ("AdaQP-q", "gcn", "random", "ogbn-products"),
+    ("AdaQP-p", "gcn", "uniform", "ogbn-products")])
 def test_parity_two_ranks(mode, model_name, scheme, dataset):
     ngpu = torch.cuda.device_count()
     res = _run(2, ngpu, mode, model_name, scheme, dataset)
-    _check(res, 2, quant=mode != "Vanilla")
+    _check(res, 2, quant=mode in ("AdaQP", "AdaQP-q"))
 
 
 @pytest.mark.parametrize("mode,model_name,scheme", [("AdaQP", "gcn", "random"), ("AdaQP", "sage", "random")])

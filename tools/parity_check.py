@@ -36,11 +36,16 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 BITS_SET = (2, 4, 8)
-# Final-layer activations, product vs reference flow, same seed: the aggregation sums in a
-# different fp32 order (our CSR kernel vs cuSPARSE) -> ~1e-6 relative differences in layer-1
-# activations -> a few stochastic-rounding decisions of later exchanges flip by one level
-# ((max-min)/(2^b-1) on one element of one halo row).  Bound on max|a-b| / max|b|:
-ACT_TOL = 2e-2
+# Final-layer activations / first-layer weight gradient, product vs reference flow, same weights,
+# bit assignment and generator seed.  The aggregation sums in a different fp32 order (our CSR kernel
+# vs cuSPARSE), which moves layer-1 activations by ~1e-6 relative; now and then that flips ONE
+# stochastic-rounding decision of a later exchange by one level ((max-min)/(2^b-1) on one element of
+# one halo row, i.e. up to a third of the row's range at 2 bits), so the MAX error is flip-dominated
+# and grows with the number of quantised elements, while the MEAN error and the loss stay at fp32
+# rounding level.  Measured on B200 (profiles/r02_parity.md): max 8.5e-6 .. 6.8e-4, mean <= 8.5e-6.
+ACT_TOL = 5e-3          # max|a - b| / max|b|   (asserted by the small-graph tests)
+ACT_MEAN_TOL = 1e-4     # sum|a - b| / sum|b|   (the bench line's `within_tolerance`, any size)
+LOSS_TOL = 1e-4         # |loss_a - loss_b| / |loss_b|
 
 
 def _windows(G: int, wg: int, n_windows: int) -> List[int]:
@@ -204,7 +209,7 @@ def current_assignment() -> Dict[str, Dict[int, torch.Tensor]]:
     return out
 
 
-def activation_parity(trainer, seed: int = 1234) -> Dict:
+def activation_parity(trainer, seed: int = 1234, overlapped: bool = False) -> Dict:
     import torch.distributed as dist
     from oracle import build as obuild
     from oracle import ref_path
@@ -227,7 +232,12 @@ def activation_parity(trainer, seed: int = 1234) -> Dict:
             return {"unavailable": "oracle/_ref/quant_cuda.so (reference kernels) not built"}
         qc = obuild.load_ref()
     dims = [cfg["data"]["num_feats"]] + [cfg["model"]["hidden_dim"]] * (cfg["model"]["num_layers"] - 1)
-    st = ref_path.RefState(eng.layout, dev, dims, quant, eng.use_parallel and W > 1, qc, kind)
+    # The reference's overlap (helper thread + side stream, ops.py:156-193) reorders execution, not
+    # arithmetic -- and reads send_messages on the side stream without an event (ops.py:164 ->
+    # op_util.py:101-110), which makes an overlapped run non-deterministic at small sizes.  The check
+    # therefore runs the reference flow in its sequential form (full_graph_propagation, ops.py:132-154);
+    # `overlapped=True` restates the helper-thread form for comparison.
+    st = ref_path.RefState(eng.layout, dev, dims, quant, bool(overlapped) and eng.use_parallel and W > 1, qc, kind)
     if quant:
         st.update_quant(current_assignment())
     ref = ref_path.make_model(kind, dims, cfg["data"]["num_classes"], cfg["model"]["dropout_rate"]).to(dev)
@@ -237,7 +247,7 @@ def activation_parity(trainer, seed: int = 1234) -> Dict:
     feats, labels, mask = eng.feats, eng.labels, eng.train_mask
     n_train = torch.LongTensor([mask.numel()])
     comm.all_reduce_sum(n_train)
-    res: Dict = {"seed": seed, "tolerance": ACT_TOL, "model": kind}
+    res: Dict = {"seed": seed, "model": kind, "reference_flow": "overlapped" if st.parallel else "sequential"}
 
     # (1) quantised halo of forward0: identical inputs on both flows => bit-identical halos
     if quant:
@@ -277,10 +287,19 @@ def activation_parity(trainer, seed: int = 1234) -> Dict:
     v = torch.tensor([float((lp - lr).abs().max()), float(lr.abs().max()),
                       float((gp - gr).abs().max()), float(gr.abs().max())], dtype=torch.float64)
     comm.all_reduce_max(v)
-    res.update({"act_max_rel_err": float(v[0] / max(float(v[1]), 1e-30)),
+    d = (lp - lr).abs()
+    sums = torch.tensor([float(d.sum()), float(lr.abs().sum()), float((d > 1e-3 * float(v[1])).sum()), float(d.numel())],
+                        dtype=torch.float64)
+    comm.all_reduce_sum(sums)
+    act_max = float(v[0] / max(float(v[1]), 1e-30))
+    act_mean = float(sums[0] / max(float(sums[1]), 1e-30))
+    res.update({"act_max_rel_err": act_max, "act_mean_rel_err": act_mean,
+                "act_frac_elems_over_1e-3": float(sums[2] / max(float(sums[3]), 1.0)),
                 "grad0_max_rel_err": float(v[2] / max(float(v[3]), 1e-30)),
                 "loss_product": loss_p, "loss_reference_flow": loss_r,
-                "within_tolerance": bool(v[0] / max(float(v[1]), 1e-30) <= ACT_TOL)})
+                "loss_rel_diff": abs(loss_p - loss_r) / max(abs(loss_r), 1e-30)})
+    res["tolerance"] = {"act_max": ACT_TOL, "act_mean": ACT_MEAN_TOL, "loss": LOSS_TOL}
+    res["within_tolerance"] = bool(act_mean <= ACT_MEAN_TOL and res["loss_rel_diff"] <= LOSS_TOL)
     st.pool.close()
     if comm.ctx.comm_buffer.p2p is not None:
         comm.ctx.comm_buffer.p2p.check_status()
