@@ -301,6 +301,10 @@ class PeerExchange:
         self.quant_plans: Dict[str, QuantPlan] = {}
         self.slab: Optional[Slab] = None
         self._lib = _lib.load()
+        # kernel-alone timings (bench / profiling only): when `profile` is set every send / receive launch is
+        # bracketed by CUDA events on its own stream; resolved by kernel_times_ms()
+        self.profile = False
+        self._prof: Dict[str, List[Tuple[torch.cuda.Event, torch.cuda.Event]]] = {"send": [], "recv": []}
 
     # ---- rendezvous ---------------------------------------------------------------
     def local_meta(self) -> dict:
@@ -428,6 +432,32 @@ class PeerExchange:
                 recv_chans=_to_device_bytes(rchans, self.device), n_recv_chans=len(self.recv_peers),
                 philox_increment=rel, wire=wire)
 
+    # ---- profiling ----------------------------------------------------------------
+    def _bracket(self, kind: str, stream):
+        if not self.profile:
+            return None
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        a = torch.cuda.Event(enable_timing=True)
+        a.record(st)
+        return (kind, st, a)
+
+    def _close(self, tok):
+        if tok is None:
+            return
+        kind, st, a = tok
+        b = torch.cuda.Event(enable_timing=True)
+        b.record(st)
+        self._prof[kind].append((a, b))
+
+    def kernel_times_ms(self, clear: bool = True) -> Dict[str, float]:
+        """Sum of the event-timed durations of the send / receive kernels since the last call."""
+        torch.cuda.synchronize(self.device)
+        out = {k: float(sum(a.elapsed_time(b) for a, b in v)) for k, v in self._prof.items()}
+        out["launches"] = {k: len(v) for k, v in self._prof.items()}
+        if clear:
+            self._prof = {"send": [], "recv": []}
+        return out
+
     # ---- launches -----------------------------------------------------------------
     def _next_seq(self, key: str) -> int:
         self.seq[key] += 1
@@ -441,11 +471,13 @@ class PeerExchange:
         assert x.dtype == torch.float32 and x.shape[1] == F and x.stride(1) == 1
         seq = self._next_seq(key)
         items = plan.items_compat if gathered else plan.items
+        tok = self._bracket("send", stream)
         rc = self._lib.adaqp_send_fp32(x.data_ptr(), x.stride(0), F, items.data_ptr(), plan.n_items,
                                        plan.chans.data_ptr(), plan.n_chans, F, seq,
                                        self._work_ptr(key, 0), self.status.data_ptr(), self.timeout_ns,
                                        _lib.stream_ptr(stream))
         _lib.check(rc, "adaqp_send_fp32")
+        self._close(tok)
         return seq
 
     def complete_recv_fp(self, key: str, stream=None) -> torch.Tensor:
@@ -477,23 +509,27 @@ class PeerExchange:
         assert x.dtype == torch.float32 and x.shape[1] == F and x.stride(1) == 1
         seq = self._next_seq(key)
         items = plan.send_items_compat if gathered else plan.send_items
+        tok = self._bracket("send", stream)
         rc = self._lib.adaqp_send_quant(x.data_ptr(), x.stride(0), F, items.data_ptr(), plan.n_send,
                                         plan.send_chans.data_ptr(), plan.n_send_chans,
                                         trace.data_ptr() if trace is not None else None,
                                         seed, base_offset, seq, self._work_ptr(key, 0),
                                         self.status.data_ptr(), self.timeout_ns, _lib.stream_ptr(stream))
         _lib.check(rc, "adaqp_send_quant")
+        self._close(tok)
         return seq
 
     def complete_recv_quant(self, key: str, stream=None) -> torch.Tensor:
         plan = self.quant_plans[key]
         F = self.dims[key]
         halo = self.halo(key)
+        tok = self._bracket("recv", stream)
         rc = self._lib.adaqp_recv_quant(halo.data_ptr(), F, F, plan.recv_items.data_ptr(), plan.n_recv,
                                         plan.recv_chans.data_ptr(), plan.n_recv_chans, self.seq[key],
                                         self._work_ptr(key, 1), self.status.data_ptr(), self.timeout_ns,
                                         _lib.stream_ptr(stream))
         _lib.check(rc, "adaqp_recv_quant")
+        self._close(tok)
         return halo
 
     def close(self):

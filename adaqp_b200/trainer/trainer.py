@@ -36,6 +36,11 @@ class Trainer(object):
         with open(cfg_path, "r") as f:
             self.config = yaml.load(f, Loader=yaml.FullLoader)
         self.config["runtime"].update({k: v for k, v in args.items() if v is not None})
+        # extension: `assign_bits` / `assign_cycle` / `group_size` given at run time override the yaml's
+        # `assignment:` section (the reference edits the yaml, e.g. assign_bits: 4 for uniform 4-bit)
+        for k in ("assign_bits", "assign_cycle", "group_size", "coe_lambda"):
+            if args.get(k) is not None:
+                self.config["assignment"][k] = args[k]
         rt = self.config["runtime"]
         self.exp_path = f"{rt['exp_path']}/{dataset}/{rt['num_parts']}part/{rt['model_name']}"
         self.logger = setup_logger("trainer.log", rt["logger_level"], with_file=True)

@@ -38,6 +38,7 @@ def parse():
     p.add_argument("--model_name", type=str, default="gcn")
     p.add_argument("--mode", type=str, default="AdaQP")
     p.add_argument("--assign_scheme", type=str, default="random")
+    p.add_argument("--assign_bits", type=int, default=None, help="uniform bit-width (overrides the yaml's assign_bits)")
     p.add_argument("--scale", type=float, default=float(os.environ.get("ADAQP_SYNTH_SCALE", "1.0")))
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-verify", action="store_true",
@@ -133,9 +134,12 @@ def spmm_algorithmic_bytes(eng, dims, use_parallel):
     return total, launches
 
 
+NVLINK_PEAK_GBPS = 770.0      # measured peer copy per direction, B200_PROFILING.md (nominal 900)
+
+
 def exchange_stats(ex, eng, traced_all):
     """Rank 0's boundary traffic per training epoch and the event-timed duration of the
-    exchange kernels (send + wait + receive, side stream): NVLink-side achieved GB/s."""
+    exchange region (send + flag wait + receive, side stream)."""
     import numpy as np
     recv_bytes = rows = 0
     for key, plan in ex.quant_plans.items():
@@ -147,9 +151,46 @@ def exchange_stats(ex, eng, traced_all):
     b = recv_bytes if recv_bytes else fp_bytes
     return {"halo_rows_per_exchange": ex.num_remote, "send_rows_per_exchange": int(eng.total_send_idx.numel()),
             "bytes_in_per_epoch": int(b), "fp32_equivalent_bytes_per_epoch": int(fp_bytes),
-            "exchange_kernels_ms_per_epoch": exch_ms, "achieved_in_GBps": b / max(exch_ms, 1e-9) / 1e6,
-            "nvlink_peak_GBps_per_direction": 770.0,
-            "note": "exchange kernels are latency/launch bound at this size; they overlap the central aggregation"}
+            "exchange_region_ms_per_epoch": exch_ms}
+
+
+def exchange_roofline(ex, eng, times, epochs, hbm_peak):
+    """Second roofline block: the send and receive kernels of the exchange, each timed ALONE with CUDA
+    events on the stream it runs on (rank 0, sums over the timed epochs), against both bounds.
+    Algorithmic bytes: send reads 4F+4 (+8 index) per boundary row from HBM and stores
+    F*b/8+4 to the peer over NVLink; receive reads F*b/8+4 per halo row and writes 4F."""
+    S = int(eng.total_send_idx.numel())
+    send_hbm = send_link = recv_hbm = 0
+    if ex.quant_plans:
+        for key, plan in ex.quant_plans.items():
+            F = ex.dims[key]
+            wire_in = sum(q + 4 * n for q, n in plan.wire.values())
+            send_hbm += S * (4 * F + 12)
+            recv_hbm += wire_in + 4 * F * ex.num_remote
+            send_link += plan.n_send * F + 4 * S     # F packed bytes per byte-row + bf16 (scale, min) per row
+        send_hbm += send_link
+    else:
+        for key in ex.keys:
+            if key.startswith("test"):
+                continue
+            F = ex.dims[key]
+            send_hbm += S * (8 * F + 16)
+            send_link += S * 4 * F
+    out = {"rank": 0, "epochs": epochs, "launches": times["launches"]}
+    if times["send"] > 0:
+        ms = times["send"] / epochs
+        out["send"] = {"kernel": "send_quant_kernel" if ex.quant_plans else "send_fp32_kernel", "ms_per_epoch": ms,
+                       "hbm_bytes_per_epoch": int(send_hbm), "hbm_GBps": send_hbm / ms / 1e6, "hbm_frac": send_hbm / ms / 1e6 / hbm_peak,
+                       "nvlink_bytes_per_epoch": int(send_link), "nvlink_GBps": send_link / ms / 1e6,
+                       "nvlink_frac": send_link / ms / 1e6 / NVLINK_PEAK_GBPS}
+    if times["recv"] > 0:
+        ms = times["recv"] / epochs
+        out["recv"] = {"kernel": "recv_quant_kernel", "ms_per_epoch": ms, "hbm_bytes_per_epoch": int(recv_hbm),
+                       "hbm_GBps": recv_hbm / ms / 1e6, "hbm_frac": recv_hbm / ms / 1e6 / hbm_peak}
+    out["peaks"] = {"hbm_GBps": hbm_peak, "nvlink_GBps_per_direction": NVLINK_PEAK_GBPS}
+    out["note"] = ("parity-mode Philox (one Philox4x32-10 block per packed byte, mandated by curand_init(seed, k, offset)) makes the "
+                   "send kernel integer-issue bound, not HBM/NVLink bound; both kernels overlap the aggregation")
+    return out
 
 
 def cpu_baseline_port(eng, dims, seconds_budget=20.0):
@@ -195,7 +236,7 @@ def run_ours(args, rank, world):
 
     targs = Namespace(dataset=args.dataset, num_parts=world, backend="gloo", init_method="env://",
                       model_name=args.model_name, mode=args.mode, assign_scheme=args.assign_scheme,
-                      logger_level="WARNING", exp_path="/tmp/adaqp_bench_exp")
+                      logger_level="WARNING", exp_path="/tmp/adaqp_bench_exp", assign_bits=getattr(args, "assign_bits", None))
     tr = Trainer(targs)
     eng = engine.ctx
     dev = comm.ctx.device
@@ -230,8 +271,18 @@ def run_ours(args, rank, world):
 
     sampler = ClockSampler(dev.index or 0)      # samples under load from the warm-up on
     sampler.start()
+    adaptive = args.assign_scheme == "adaptive" and tr.assigner.is_tracing
+    if adaptive:
+        # adaptive re-assignment (runtime_util.py:86-93) happens when epoch % assign_cycle == 1: trace two
+        # epochs at the uniform warm-up width, let the third warm-up epoch solve + re-allocate (untimed),
+        # then freeze the assignment for the timed region
+        tr.assigner.assign_cycle = 3
     for _ in range(max(args.warmup, 3)):
         step(eng.feats, eng.labels)
+    if adaptive:
+        tr.assigner.assign_cycle = 10 ** 9
+        for _ in range(2):
+            step(eng.feats, eng.labels)
     exposed, agg_s = [], []
 
     def dev_step():
@@ -240,7 +291,14 @@ def run_ours(args, rank, world):
         agg_s.append(traced[3] + traced[4] + traced[5])
         return traced
 
+    p2p = comm.ctx.comm_buffer.p2p
+    if p2p is not None:
+        p2p.profile = True
     ms, traced_all = timed(args.steps, dev_step)
+    exch_times = None
+    if p2p is not None:
+        exch_times = p2p.kernel_times_ms()
+        p2p.profile = False
     # ---- end-to-end: host inputs -> device every step, loss read back
     feats_host = eng.feats.cpu().pin_memory()
     labels_host = eng.labels.cpu().pin_memory()
@@ -284,10 +342,14 @@ def run_ours(args, rank, world):
     dist.all_reduce(gl, op=dist.ReduceOp.MAX)
     peaks, peak_kind = measured_peaks()
     achieved = alg_bytes / (agg_ms * 1e-3) / 1e9
-    traffic = None
+    # dram__bytes_read + dram__bytes_write per launch from an `ncu --set full` capture of THIS workload at THIS N
+    # (profiles/spmm_traffic.json, keyed by n_gpus; per-shape figures next to it); null where none was taken
+    traffic = traffic_detail = None
     tpath = os.path.join(ROOT, "profiles", "spmm_traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    if os.path.exists(tpath) and args.dataset == "ogbn-products" and args.scale == 1.0:
+        ent = json.load(open(tpath)).get("by_n_gpus", {}).get(str(world))
+        if ent:
+            traffic, traffic_detail = ent.get("dram_bytes_per_launch_mean"), ent.get("per_shape")
     n_exch = 5 if world > 1 else 0
     # our kernels per epoch: aggregation launches (the marginal rows take two passes -- local then halo
     # segment -- unless ADAQP_MARGINAL_SPLIT=0) + per exchange: send, flag wait, receive (quant) or
@@ -309,15 +371,19 @@ def run_ours(args, rank, world):
                 "api": "train_for_one_epoch on inputs copied from pinned host memory every step (double-buffered prefetch on a copy stream), loss.item()"},
         "gpu_launches": int(launches_per_epoch * args.steps),
         "roofline": {"kernel": "spmm_csr_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
-                     "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_kind": f"of {peak_kind}",
+                     "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_per_shape": traffic_detail, "peak_kind": f"of {peak_kind}",
                      "algorithmic_bytes_per_epoch": alg_bytes, "launches_per_epoch": launches, "spmm_ms_per_epoch": agg_ms,
                      "gather_bound": {"note": "no-reuse bound 4*F*nnz: what a random gather must move when the source matrix exceeds L2",
                                       "achieved_GBps": sum(4 * F * int(eng.layout.indptr[-1]) for F in [dims[0], dims[1], dims[2], dims[2], dims[1]]) / (agg_ms * 1e-3) / 1e9}},
         "final_loss": losses[-1],
         "exchange": exchange_stats(comm.ctx.comm_buffer.p2p, eng, traced_all) if world > 1 else None,
+        "roofline_exchange": exchange_roofline(comm.ctx.comm_buffer.p2p, eng, exch_times, args.steps, peaks["hbm_gbs"]) if world > 1 else None,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_port(eng, dims)
+    hook = getattr(args, "before_teardown", None)     # tools/run_configs.py: hand the layout / assignment to the reference arm
+    if hook is not None:
+        hook(tr)
     if not args.no_verify:
         # outside the timed region: what the peers wrote into my slab over NVLink vs the CPU oracle
         # (bit-exact), and one training step vs the reference flow around the reference's own kernels

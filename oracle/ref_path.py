@@ -410,7 +410,9 @@ def bench(args, rank, world):
         return out
 
     kind = args.model_name
-    L = prepare_rank(spec, rank, DistGNNType.DistGCN if kind == "gcn" else DistGNNType.DistSAGE, gather)
+    L = getattr(args, "layout", None)                      # a layout already prepared in this process (run_configs)
+    if L is None:
+        L = prepare_rank(spec, rank, DistGNNType.DistGCN if kind == "gcn" else DistGNNType.DistSAGE, gather)
     dims = [cfg["data"]["num_feats"]] + [cfg["model"]["hidden_dim"]] * (cfg["model"]["num_layers"] - 1)
     st = RefState(L, dev, dims, quant, parallel, qc, kind)
     torch.manual_seed(2024)
@@ -418,9 +420,14 @@ def bench(args, rank, world):
     if quant and world > 1:
         keys = [f"forward{i}" for i in range(len(dims))] + [f"backward{i}" for i in range(1, len(dims))]
         bits = torch.tensor(BITS_SET, dtype=torch.int32)
-        assign = {k: {p: (bits[torch.multinomial(torch.full((3,), 1 / 3), hi - lo, replacement=True)] if args.assign_scheme == "random"
-                          else torch.full((hi - lo,), cfg["assignment"]["assign_bits"], dtype=torch.int32))
-                      for p, (lo, hi) in L.send_idx.items()} for k in keys}
+        ubits = getattr(args, "assign_bits", None) or cfg["assignment"]["assign_bits"]
+        given = getattr(args, "assignment", None)          # e.g. the product arm's adaptive result (tools/run_configs.py)
+        if given is not None:
+            assign = given
+        else:                                              # 'adaptive' without a given result: random {2,4,8} stands in
+            assign = {k: {p: (torch.full((hi - lo,), ubits, dtype=torch.int32) if args.assign_scheme == "uniform"
+                              else bits[torch.multinomial(torch.full((3,), 1 / 3), hi - lo, replacement=True)])
+                          for p, (lo, hi) in L.send_idx.items()} for k in keys}
         st.update_quant(assign)
     model = make_model(kind, dims, cfg["data"]["num_classes"], cfg["model"]["dropout_rate"]).to(dev)
     for v in model.state_dict().values():
