@@ -29,6 +29,9 @@ from .buffer import Basic_Buffer_Type, CommBuffer
 logger = logging.getLogger("trainer")
 
 
+_EXIT_HOOK = False
+
+
 def _pick_device(local_rank: int) -> torch.device:
     want = os.environ.get("ADAQP_DEVICE", "").lower()
     if want == "cpu":
@@ -52,6 +55,11 @@ class Communicator(object):
             raise NotImplementedError("only gloo is supported now")
         if not dist.is_initialized():
             dist.init_process_group(backend, init_method=init_method)
+        global _EXIT_HOOK
+        if not _EXIT_HOOK:
+            import atexit
+            atexit.register(Communicator._destroy)
+            _EXIT_HOOK = True
         self._backend = backend
         self._init_method = init_method
         self._local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -87,10 +95,10 @@ class Communicator(object):
             dist.destroy_process_group()
 
     def __del__(self):
-        try:
-            self._destroy()
-        except Exception:
-            pass
+        # The reference destroys the process group in __del__ (comm.py:230-233).  Here the group outlives
+        # any one communicator object (a process may build several Trainers in a row, and object
+        # finalisation order is not under our control): it is destroyed once, at interpreter exit.
+        pass
 
     @staticmethod
     def barrier():
