@@ -147,7 +147,9 @@ class Assigner(object):
                 v = dict(chain(*[p[0][key].items() for p in params_list]))
                 c = dict(chain(*[p[1][key].items() for p in params_list]))
                 t0 = time.time()
-                layer_assign[key], _ = solver.solve_layer(v, c, model, coe_lambda, W)
+                # 'p2p': one send launch per rank writes all peers (max over ranks); 'gloo': the reference's ring rounds
+                schedule = "concurrent" if comm.ctx.transport == "p2p" else "ring"
+                layer_assign[key], _ = solver.solve_layer(v, c, model, coe_lambda, W, schedule=schedule)
                 self.last_solve_seconds[key] = time.time() - t0
                 logger.info(f"layer {key} solving time: {self.last_solve_seconds[key]:.4f}s")
             per_rank = []

@@ -1,10 +1,18 @@
 """alpha-beta cost model of every (src, dst) channel: time_ms = alpha * MB + beta.
 
 Reference: AdaQP/assigner/profile.py:18-106 times 200 `dist.send` payloads per peer pair
-over gloo and fits a line with np.polyfit.  Here the payload sizes and the fit are the
-same, but on the 'p2p' transport the timed operation is the thing the exchange actually
-does: a device-to-peer-slab copy over NVLink (CUDA events), so that `adaptive` optimises
-the transport in use.  On the 'gloo' transport the reference's send/recv timing is kept.
+over gloo and fits a line with np.polyfit; that is kept for the 'gloo' transport.
+
+On the 'p2p' transport the thing being modelled is the real exchange: ONE
+`send_quant_kernel` launch per rank quantises, packs and stores to ALL peers, and one
+`recv_quant_kernel` launch dequantises what arrived.  Both are issue-bound on the packed
+bytes (one Philox block per byte), not link-bound, so a peer-copy timing says nothing
+about them (round 1 timed `copy_` to the peer slab: at full scale the fitted slope was
+~0 and `adaptive` chose 8 bits everywhere).  `_profile_p2p` therefore runs the real
+kernel pair at uniform 2 / 4 / 8 bits for both layer widths, times each kernel ALONE with
+CUDA events, and fits time = alpha * (MB this rank sends) + beta per RANK; every channel of
+the rank carries the rank's (alpha, beta) and the solver's 'concurrent' schedule charges
+the rank alpha * (MB of all its channels) + beta (assigner/solver.py).
 """
 from __future__ import annotations
 
@@ -30,47 +38,52 @@ def payload_sizes(num_nodes: int, feat_dim: int, hidden_dim: int, num_data: int)
 
 def fit_cost_model(dataset: Tuple[Dict[str, np.ndarray], Dict[str, np.ndarray]]) -> Dict[str, np.ndarray]:
     sizes_mb, times_ms = dataset
-    return {k: np.polyfit(np.asarray(sizes_mb[k], np.float64), np.asarray(times_ms[k], np.float64), 1)
-            for k in sizes_mb}
+    out = {}
+    for k in sizes_mb:
+        x, y = np.asarray(sizes_mb[k], np.float64), np.asarray(times_ms[k], np.float64)
+        ab = np.polyfit(x, y, 1) if np.ptp(x) > 0 else np.array([0.0, float(y.mean())])
+        out[k] = ab
+    return out
 
 
-def _profile_p2p(feat_dim, hidden_dim, num_data, warmup):
-    ex = comm.ctx.comm_buffer.p2p
+def _profile_p2p(feat_dim, hidden_dim, num_data, warmup, reps: int = 5):
+    """Per-rank (alpha, beta) of the real send + receive kernel pair.  Collective: every rank runs the
+    same sequence of buffer updates and exchanges.  `num_data` (the reference's number of payload sizes)
+    is not needed: the payloads are the three uniform bit-widths x two layer widths of the real plan."""
+    buf = comm.ctx.comm_buffer
+    ex = buf.p2p
     rank = comm.get_rank()
-    sizes_mb, times_ms = {}, {}
     dev = comm.ctx.device
-    key = ex.keys[-1]
-    for p, (lo, hi) in ex.send_idx.items():
-        sizes = payload_sizes(hi - lo, feat_dim, hidden_dim, num_data)
-        cap = ex.layouts[p].halo_off[key]                     # write into the peer's halo block of the last key
-        room = 4 * ex.dims[key] * max(ex.layouts[p].num_remote, 1)
-        src = torch.zeros(int(min(sizes.max(), room)), dtype=torch.uint8, device=dev)
-        dst = _peer_view(ex, p, cap, src.numel())
-        ts = []
-        for n in sizes:
-            n = int(min(n, src.numel()))
-            for _ in range(warmup):
-                dst[:n].copy_(src[:n])
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(2 * warmup):
-                dst[:n].copy_(src[:n])
-            b.record()
-            b.synchronize()
-            ts.append(a.elapsed_time(b) / (2 * warmup))
-        sizes_mb[f"{rank}_{p}"] = np.minimum(sizes, src.numel()) / (1024 ** 2)
-        times_ms[f"{rank}_{p}"] = np.asarray(ts)
+    n_inner = engine.ctx.num_inner
+    keys = [("forward0", feat_dim), ("forward1", hidden_dim)] if len(ex.buffer_shape) > 1 else [("forward0", feat_dim)]
+    xs = {k: torch.relu(torch.randn(n_inner, F, device=dev)) for k, F in keys}
+    S = int(sum(hi - lo for lo, hi in ex.send_idx.values()))
+    mbs, ts = [], []
+    was = ex.profile
+    for b in BITS_SET:
+        assign = {k: {p: torch.full((hi - lo,), b, dtype=torch.int32) for p, (lo, hi) in ex.send_idx.items()} for k, _ in keys}
+        buf._update(assign)
+        for k, F in keys:
+            for it in range(warmup + reps):
+                if it == warmup:
+                    torch.cuda.synchronize(dev)
+                    comm.barrier()
+                    ex.profile = True
+                    ex.kernel_times_ms()
+                ex.post_send_quant(k, xs[k], 1234, 0)
+                ex.wait_flags_quant(k)
+                ex.complete_recv_quant(k)
+            t = ex.kernel_times_ms()
+            ex.profile = False
+            mbs.append(S * F * b / 8 / (1024 ** 2))
+            ts.append((t["send"] + t["recv"]) / reps)
+    ex.profile = was
+    ex.check_status()
+    buf._delete_train_buffer()
     comm.barrier()
+    sizes_mb = {f"{rank}_{p}": np.asarray(mbs) for p in ex.send_idx}
+    times_ms = {f"{rank}_{p}": np.asarray(ts) for p in ex.send_idx}
     return sizes_mb, times_ms
-
-
-def _peer_view(ex, p: int, offset: int, nbytes: int) -> torch.Tensor:
-    class _H:
-        pass
-    h = _H()
-    h.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1",
-                                  "data": (ex.peer_base[p] + offset, False), "version": 2}
-    return torch.as_tensor(h, device=ex.device)
 
 
 def _profile_gloo(feat_dim, hidden_dim, num_data, warmup):

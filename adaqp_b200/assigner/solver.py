@@ -22,6 +22,15 @@ Structure exploited (an exact reformulation, not a heuristic):
     global optimum.
 `brute_force` enumerates all assignments of tiny instances and is used by the tests to
 confirm optimality (no MIP solver is installed to compare with).
+
+Schedules.  'ring' is the reference's model of the gloo transport: W-1 rounds, round r
+carries the channels rank -> (rank + r) % W and costs the slowest of them, the epoch pays
+sum_r Z_r.  'concurrent' models the P2P transport of this repo: ONE send launch per rank
+writes all of its peers at once, so a rank's exchange costs alpha_s * (MB of ALL its
+channels) + beta_s (alpha/beta fitted on the real send + receive kernel pair,
+assigner/profile.py) and the layer pays max over ranks: a single "round" whose units are
+the sender ranks.  Pooling a sender's channels keeps the structure above, because groups
+of one layer cost the same bytes per bit-width in every channel.
 """
 from __future__ import annotations
 
@@ -33,15 +42,38 @@ import numpy as np
 BITS = (2, 4, 8)
 
 
-def _scales(var_matrix, comm_matrix, cost_model, world_size: int):
+def _rounds(keys, world_size: int, schedule: str) -> List[List[str]]:
+    """Groups of units that run concurrently; the layer pays the sum over groups of the slowest unit."""
+    if schedule == "ring":
+        out = []
+        for r in range(1, world_size):
+            chans = [f"{rank}_{(rank + r) % world_size}" for rank in range(world_size)]
+            out.append([c for c in chans if c in keys])
+        return [g for g in out if g]
+    if schedule == "concurrent":
+        return [sorted(keys, key=lambda k: int(k))]
+    raise ValueError(f"unknown schedule {schedule!r}")
+
+
+def _pool_by_sender(var_matrix, comm_matrix, cost_model):
+    """'concurrent' schedule: one unit per sender rank = its channels side by side."""
+    by: Dict[str, List[str]] = {}
+    for c in var_matrix:
+        by.setdefault(c.split("_")[0], []).append(c)
+    v = {s: np.concatenate([np.asarray(var_matrix[c], np.float64) for c in cs], axis=1) for s, cs in by.items()}
+    m = {s: np.concatenate([np.asarray(comm_matrix[c], np.float64) for c in cs], axis=1) for s, cs in by.items()}
+    k = {s: np.asarray(cost_model[cs[0]], np.float64) for s, cs in by.items()}
+    return v, m, k, by
+
+
+def _scales(var_matrix, comm_matrix, cost_model, world_size: int, schedule: str = "ring"):
     """nadir / utopia of both objectives (assigner.py:344-364, 'nadir_utopia' mode)."""
     var_nadir = sum(float(np.sum(v[0])) for v in var_matrix.values())
     var_utopia = sum(float(np.sum(v[-1])) for v in var_matrix.values())
     t_nadir = t_utopia = 0.0
-    for r in range(1, world_size):
+    for group in _rounds(set(var_matrix), world_size, schedule):
         hi, lo = float("-inf"), float("inf")
-        for rank in range(world_size):
-            key = f"{rank}_{(rank + r) % world_size}"
+        for key in group:
             a, b = cost_model[key][0], cost_model[key][1]
             hi = max(hi, a * float(np.sum(comm_matrix[key][-1])) + b)
             lo = min(lo, a * float(np.sum(comm_matrix[key][0])) + b)
@@ -73,18 +105,29 @@ def _channel_frontier(var_c: np.ndarray, comm_c: np.ndarray, alpha: float, beta:
 
 
 def solve_layer(var_matrix: Dict[str, np.ndarray], comm_matrix: Dict[str, np.ndarray],
-                cost_model: Dict[str, np.ndarray], coe_lambda: float, world_size: int):
+                cost_model: Dict[str, np.ndarray], coe_lambda: float, world_size: int, schedule: str = "ring"):
     """Optimal group assignment of one layer: {channel: int32[G] bits}, objective value."""
-    (vn, vu), (tn, tu) = _scales(var_matrix, comm_matrix, cost_model, world_size)
+    if schedule == "concurrent":
+        v, m, k, by = _pool_by_sender(var_matrix, comm_matrix, cost_model)
+        pooled, objective = _solve_units(v, m, k, coe_lambda, world_size, "concurrent")
+        result = {}
+        for s, cs in by.items():
+            off = 0
+            for c in cs:
+                G = np.asarray(var_matrix[c]).shape[1]
+                result[c] = pooled[s][off:off + G].copy()
+                off += G
+        return result, objective
+    return _solve_units(var_matrix, comm_matrix, cost_model, coe_lambda, world_size, schedule)
+
+
+def _solve_units(var_matrix, comm_matrix, cost_model, coe_lambda: float, world_size: int, schedule: str):
+    (vn, vu), (tn, tu) = _scales(var_matrix, comm_matrix, cost_model, world_size, schedule)
     a = coe_lambda / (vn - vu) if vn > vu else 0.0
     b = (1.0 - coe_lambda) / (tn - tu) if tn > tu else 0.0
     result: Dict[str, np.ndarray] = {}
     objective = -a * vu - b * tu
-    for r in range(1, world_size):
-        chans = [f"{rank}_{(rank + r) % world_size}" for rank in range(world_size)]
-        chans = [c for c in chans if c in var_matrix]
-        if not chans:
-            continue
+    for chans in _rounds(set(var_matrix), world_size, schedule):
         fr = {c: _channel_frontier(np.asarray(var_matrix[c], np.float64), np.asarray(comm_matrix[c], np.float64),
                                    float(cost_model[c][0]), float(cost_model[c][1])) for c in chans}
         z_min = max(f[0][0] for f in fr.values())
@@ -115,8 +158,17 @@ def solve_layer(var_matrix: Dict[str, np.ndarray], comm_matrix: Dict[str, np.nda
     return result, objective
 
 
-def objective_value(assign: Dict[str, np.ndarray], var_matrix, comm_matrix, cost_model, coe_lambda, world_size):
-    (vn, vu), (tn, tu) = _scales(var_matrix, comm_matrix, cost_model, world_size)
+def objective_value(assign: Dict[str, np.ndarray], var_matrix, comm_matrix, cost_model, coe_lambda, world_size,
+                    schedule: str = "ring"):
+    if schedule == "concurrent":
+        v, m, k, by = _pool_by_sender(var_matrix, comm_matrix, cost_model)
+        pooled = {s: np.concatenate([np.asarray(assign[c]) for c in cs]) for s, cs in by.items()}
+        return _objective_units(pooled, v, m, k, coe_lambda, world_size, "concurrent")
+    return _objective_units(assign, var_matrix, comm_matrix, cost_model, coe_lambda, world_size, schedule)
+
+
+def _objective_units(assign, var_matrix, comm_matrix, cost_model, coe_lambda, world_size, schedule):
+    (vn, vu), (tn, tu) = _scales(var_matrix, comm_matrix, cost_model, world_size, schedule)
     row = {2: 0, 4: 1, 8: 2}
     var = 0.0
     times = {}
@@ -127,16 +179,14 @@ def objective_value(assign: Dict[str, np.ndarray], var_matrix, comm_matrix, cost
         mb = float(np.sum(np.asarray(comm_matrix[c])[rows, g]))
         times[c] = cost_model[c][0] * mb + cost_model[c][1]
     zsum = 0.0
-    for r in range(1, world_size):
-        ts = [times[f"{k}_{(k + r) % world_size}"] for k in range(world_size) if f"{k}_{(k + r) % world_size}" in times]
-        if ts:
-            zsum += max(ts)
+    for group in _rounds(set(times), world_size, schedule):
+        zsum += max(times[c] for c in group)
     a = coe_lambda / (vn - vu) if vn > vu else 0.0
     b = (1.0 - coe_lambda) / (tn - tu) if tn > tu else 0.0
     return a * (var - vu) + b * (zsum - tu)
 
 
-def brute_force(var_matrix, comm_matrix, cost_model, coe_lambda, world_size):
+def brute_force(var_matrix, comm_matrix, cost_model, coe_lambda, world_size, schedule: str = "ring"):
     """Enumerate every assignment (tests only; 3^(total groups) candidates)."""
     chans = list(var_matrix)
     sizes = [np.asarray(var_matrix[c]).shape[1] for c in chans]
@@ -146,7 +196,7 @@ def brute_force(var_matrix, comm_matrix, cost_model, coe_lambda, world_size):
         for c, n in zip(chans, sizes):
             assign[c] = np.array(combo[k:k + n], np.int32)
             k += n
-        val = objective_value(assign, var_matrix, comm_matrix, cost_model, coe_lambda, world_size)
+        val = objective_value(assign, var_matrix, comm_matrix, cost_model, coe_lambda, world_size, schedule)
         if best is None or val < best - 1e-15:
             best, best_assign = val, assign
     return best_assign, best

@@ -36,6 +36,8 @@ class Trainer(object):
         with open(cfg_path, "r") as f:
             self.config = yaml.load(f, Loader=yaml.FullLoader)
         self.config["runtime"].update({k: v for k, v in args.items() if v is not None})
+        if os.environ.get("ADAQP_NUM_EPOCHES"):          # short runs of the unmodified reference main.py (no such flag there)
+            self.config["runtime"]["num_epoches"] = int(os.environ["ADAQP_NUM_EPOCHES"])
         # extension: `assign_bits` / `assign_cycle` / `group_size` given at run time override the yaml's
         # `assignment:` section (the reference edits the yaml, e.g. assign_bits: 4 for uniform 4-bit)
         for k in ("assign_bits", "assign_cycle", "group_size", "coe_lambda"):

@@ -49,3 +49,43 @@ def test_extremes():
     for k, b in all2.items():
         t = model[k][0] * sum(com[k][{2: 0, 4: 1, 8: 2}[int(x)], i] for i, x in enumerate(b)) + model[k][1]
         assert t <= z + 1e-12
+
+
+@pytest.mark.parametrize("W,groups,lam", [(2, [2, 3], 0.5), (3, [1, 1, 2, 1, 1, 1], 0.5), (3, [1], 0.3), (2, [3, 2], 0.9)])
+def test_concurrent_schedule_matches_bruteforce(W, groups, lam):
+    """P2P transport model: one send launch per rank writes all peers, the layer pays the slowest RANK
+    (alpha_rank * MB of all its channels + beta_rank) -- solver vs exhaustive enumeration."""
+    rng = np.random.default_rng(7 * W + len(groups) + int(lam * 10))
+    var, com, model = instance(W, groups, rng)
+    for s in range(W):                       # all channels of a sender share the sender's (alpha, beta)
+        ab = np.array([rng.uniform(50, 400), rng.uniform(0.001, 0.05)])
+        for d in range(W):
+            if s != d:
+                model[f"{s}_{d}"] = ab
+    got, obj = solver.solve_layer(var, com, model, lam, W, schedule="concurrent")
+    _, want = solver.brute_force(var, com, model, lam, W, schedule="concurrent")
+    val = solver.objective_value(got, var, com, model, lam, W, schedule="concurrent")
+    assert abs(val - obj) < 1e-9
+    assert val <= want + 1e-9, (val, want)
+    assert set(got) == set(var)
+    for key, bits in got.items():
+        assert bits.shape == (var[key].shape[1],) and set(bits.tolist()) <= {2, 4, 8}
+
+
+def test_concurrent_differs_from_ring_when_it_should():
+    """Three ranks, rank 0 sends far more than the others: under the ring model every round is bounded by
+    a rank-0 channel; under the concurrent model only rank 0's total matters, so ranks 1 and 2 keep 8 bits."""
+    rng = np.random.default_rng(3)
+    var, com, model = {}, {}, {}
+    for s in range(3):
+        for d in range(3):
+            if s == d:
+                continue
+            G = 6 if s == 0 else 1
+            v = np.sort(rng.gamma(1.0, 1.0, G))[::-1]
+            var[f"{s}_{d}"] = COST[:, None] * v[None, :]
+            com[f"{s}_{d}"] = np.repeat(np.array([2, 4, 8], float)[:, None] * 64 * 10 / 8 / 2 ** 20, G, axis=1)
+            model[f"{s}_{d}"] = np.array([200.0, 0.001])
+    got, _ = solver.solve_layer(var, com, model, 0.5, 3, schedule="concurrent")
+    assert all(np.all(got[f"{s}_{d}"] == 8) for s in (1, 2) for d in range(3) if d != s)
+    assert any(np.any(got[f"0_{d}"] < 8) for d in (1, 2))
