@@ -43,6 +43,7 @@ class SynthSpec:
     community_size: int = 4096
     homophily: float = 0.6
     feature_signal: float = 0.5
+    label_noise: float = 0.05
     train_fraction: float = 0.5
     val_fraction: float = 0.1
     seed: int = 0
@@ -69,6 +70,7 @@ def spec_from_config(config: dict, num_parts: int, scale: float = 1.0) -> SynthS
                      community_size=int(s.get("community_size", 4096)),
                      homophily=float(s.get("homophily", 0.6)),
                      feature_signal=float(os.environ.get("ADAQP_SYNTH_SIGNAL", s.get("feature_signal", 0.5))),
+                     label_noise=float(os.environ.get("ADAQP_SYNTH_LABEL_NOISE", s.get("label_noise", 0.05))),
                      train_fraction=float(s["train_fraction"]), val_fraction=float(s["val_fraction"]),
                      seed=int(s.get("seed", 0)))
     return spec.scaled(scale) if scale != 1.0 else spec
@@ -193,7 +195,7 @@ def _node_data(spec: SynthSpec, p: int, n: int):
     C, F = spec.num_classes, spec.num_feats
     comm = np.arange(n) // cs
     cls = ((comm + 7 * p) % C).astype(np.int64)
-    flip = rng.random(n) < 0.05                      # label noise
+    flip = rng.random(n) < spec.label_noise          # label noise
     cls[flip] = rng.integers(0, C, int(flip.sum()))
     cent = np.random.default_rng(spec.seed + 977).standard_normal((C, F)).astype(np.float32)
     feat = rng.standard_normal((n, F), dtype=np.float32)

@@ -164,3 +164,33 @@ def test_side_by_side_with_reference_kernels(qc, N, F, bits):
     da = ref.unpack_single_precision(a, bits, scale, rmin, N, F)
     db = qc.unpack_single_precision(b, bits, scale, rmin, N, F)
     assert torch.equal(da, db)
+
+
+def test_dtype_boundary_matches_reference_checks():
+    """check.h:22-27 admits float32 and float16 and rejects everything else with
+    'The type of <name> is not correct!' (the fp64 kernel instantiation of
+    quantization_cuda_kernel.cu:81 is unreachable behind that check).  This library builds the fp32
+    instantiation only -- the dtype of every boundary message on the hot path (op_util.py:72) -- and
+    refuses float16 explicitly instead of computing in another precision."""
+    from adaqp_b200 import quant
+    dev = torch.device("cuda:0")
+    x = torch.randn(8, 32, device=dev)
+    mn, mx = x.min(1)[0], x.max(1)[0]
+    sc = 15.0 / (mx - mn)
+    for bad in (torch.float64, torch.bfloat16, torch.int32):
+        with pytest.raises(RuntimeError, match="The type of data is not correct!"):
+            quant.pack_single_precision(x.to(bad), mn, mx, sc, 4, True)
+    with pytest.raises(RuntimeError, match="The type of scale is not correct!"):
+        quant.pack_single_precision(x, mn, mx, sc.double(), 4, True)
+    with pytest.raises(RuntimeError, match="only the float32 instantiation"):
+        quant.pack_single_precision(x.half(), mn.half(), mx.half(), sc.half(), 4, True)
+    q = quant.pack_single_precision(x, mn, mx, sc, 4, True)
+    with pytest.raises(RuntimeError, match="only the float32 instantiation"):
+        quant.unpack_single_precision(q, 4, sc.half(), mn.half(), 8, 32)
+    with pytest.raises(RuntimeError, match="The type of scale is not correct!"):
+        quant.unpack_single_precision(q, 4, sc.double(), mn, 8, 32)
+    gen = torch.cuda.default_generators[0]
+    off = gen.get_offset()
+    with pytest.raises(RuntimeError):
+        quant.pack_single_precision(x.half(), mn.half(), mx.half(), sc.half(), 4, True)
+    assert gen.get_offset() == off, "a refused call must not consume the generator"
