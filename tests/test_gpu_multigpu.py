@@ -136,3 +136,80 @@ def test_parity_across_physical_gpus(mode, model_name, scheme):
     if world == 2:
         assert res["nccl"]["bit_exact"], res["nccl"]
     assert res["nccl"]["max_rel"] <= 1e-6, res["nccl"]
+
+
+def _evalcache_worker(rank, world, port, tmp, ngpu, out):
+    os.environ.update({"MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port), "RANK": str(rank), "WORLD_SIZE": str(world),
+                       "LOCAL_RANK": str(rank % ngpu), "ADAQP_SYNTH_SCALE": "0.004", "ADAQP_SEED": "3", "ADAQP_SYNTHETIC": "1"})
+    sys.path.insert(0, ROOT)
+    os.chdir(tmp)
+    from argparse import Namespace
+    from adaqp_b200 import Trainer
+    from adaqp_b200.communicator import Communicator as comm
+    from adaqp_b200.manager import GraphEngine as engine
+    from adaqp_b200.trainer import runtime_util as ru
+    tr = Trainer(Namespace(dataset="ogbn-products", num_parts=world, backend="gloo", init_method="env://", model_name="gcn",
+                           mode="AdaQP", assign_scheme="uniform", logger_level="WARNING", num_epoches=2, exp_path=f"{tmp}/exp"))
+    ru.sync_seed()
+    tr.model.reset_parameters()
+    ru.sync_model(tr.model)
+    eng, ex = engine.ctx, comm.ctx.comm_buffer.p2p
+    tr.model.eval()
+
+    def fwd():
+        with torch.no_grad():
+            y = tr.model(eng.graph, eng.feats).clone()
+        eng.timer.clear(is_train=False)
+        torch.cuda.synchronize()
+        return y
+
+    res = {}
+    s0 = ex.seq["test0"]
+    a = fwd()                                   # computes and caches the layer-0 exchange + aggregation
+    s1 = ex.seq["test0"]
+    b = fwd()                                   # hit: no layer-0 exchange
+    s2 = ex.seq["test0"]
+    res["first_pass_exchanged"] = s1 - s0 == 1
+    res["hit_skips_exchange"] = s2 == s1
+    res["hit_bit_exact"] = bool(torch.equal(a, b))
+    os.environ["ADAQP_EVAL_CACHE"] = "0"
+    c = fwd()                                   # cache off: recomputed
+    del os.environ["ADAQP_EVAL_CACHE"]
+    res["uncached_bit_exact"] = bool(torch.equal(a, c)) and ex.seq["test0"] == s2 + 1
+    eng.feats[: eng.feats.shape[0] // 2] += 0.25       # in-place mutation bumps the version counter
+    s3 = ex.seq["test0"]
+    d = fwd()
+    res["mutation_invalidates"] = ex.seq["test0"] == s3 + 1 and not torch.equal(a, d)
+    os.environ["ADAQP_EVAL_CACHE"] = "0"
+    e = fwd()
+    del os.environ["ADAQP_EVAL_CACHE"]
+    res["after_mutation_bit_exact"] = bool(torch.equal(d, e))
+    other = eng.feats.clone()                           # a DIFFERENT tensor never hits (identity, not address)
+    with torch.no_grad():
+        f = tr.model(eng.graph, other)
+    eng.timer.clear(is_train=False)
+    res["other_tensor_recomputed"] = bool(torch.equal(f, d))
+    ex.check_status()
+    torch.cuda.synchronize()
+    comm.ctx.delete_buffer()
+    out.put((rank, res))
+
+
+def test_eval_layer0_cache_on_gpu():
+    """the evaluation forward's constant layer-0 exchange + aggregation is cached; the cached
+    output equals the recomputed one bit for bit, the cached pass does not exchange, and an in-place change of
+    the feature matrix invalidates it (trainer.py:181 evaluates every epoch)."""
+    ngpu = torch.cuda.device_count()
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    with tempfile.TemporaryDirectory() as tmp:
+        procs = [ctx.Process(target=_evalcache_worker, args=(r, 2, port, tmp, ngpu, out)) for r in range(2)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(timeout=600)
+        assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+        res = dict(out.get(timeout=5) for _ in procs)
+    for r in (0, 1):
+        assert all(res[r].values()), res[r]

@@ -51,6 +51,10 @@ def worker(a):
             from adaqp_b200.manager import GraphEngine as engine
             from tools.parity_check import current_assignment
             shared["layout"] = engine.ctx.layout
+            cm = getattr(tr.assigner, "cost_model", None)
+            if cm:
+                k = sorted(cm)[0]
+                shared["cost_model"] = {"channel": k, "alpha_ms_per_MB": float(cm[k][0]), "beta_ms": float(cm[k][1])}
             if engine.ctx.bit_type == BitType.QUANT:
                 shared["assignment"] = current_assignment()
                 bits = torch.cat([b for per in shared["assignment"].values() for b in per.values()])
@@ -76,6 +80,8 @@ def worker(a):
                     rec["config_name"] = name
                     if arm == "ours" and "bits_share" in shared:
                         rec["assigned_bits_share_rank0"] = shared["bits_share"]
+                    if arm == "ours" and "cost_model" in shared:
+                        rec["cost_model_rank0"] = shared["cost_model"]
                     print(json.dumps(rec), flush=True)
                     if a.out:
                         os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
