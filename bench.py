@@ -193,32 +193,36 @@ def exchange_roofline(ex, eng, times, epochs, hbm_peak):
     return out
 
 
-def cpu_baseline_port(eng, dims, seconds_budget=20.0):
-    """Oracle (C port) of the hot path on the host cores: aggregation over a bounded sample of
-    destination rows, extrapolated to one epoch's five aggregations."""
+def cpu_baseline_port(eng, dims, seconds_budget=15.0):
+    """Oracle (C port) of the hot path on the host cores: the five aggregations of one epoch over a bounded,
+    evenly spaced sample of destination rows (sized from a probe so that the leg takes ~`seconds_budget`
+    seconds), extrapolated to the whole epoch by rows."""
     import numpy as np
     from oracle import oracle as O
     L = eng.layout
     n = L.n_inner
-    sample = max(1, min(n, 4096))
-    rows = np.linspace(0, n - 1, sample).astype(np.int64)
-    ip = np.concatenate([[0], np.cumsum(np.diff(L.indptr)[rows])]).astype(np.int64)
-    ix = np.concatenate([L.indices[L.indptr[r]:L.indptr[r + 1]] for r in rows]).astype(np.int64)
+    passes = [dims[0], dims[1], dims[2], dims[2], dims[1]]
     rng = np.random.default_rng(0)
-    t_epoch = 0.0
-    spent = 0.0
-    for F in [dims[0], dims[1], dims[2], dims[2], dims[1]]:
-        x = rng.standard_normal((L.n_inner + L.n_halo, F), dtype=np.float32)
-        pre = np.ones(L.n_inner + L.n_halo, np.float32)
+    n_src = L.n_inner + L.n_halo
+    xs = {F: rng.standard_normal((n_src, F), dtype=np.float32) for F in set(passes)}
+    pre = np.ones(n_src, np.float32)
+
+    def run(sample):
+        rows = np.linspace(0, n - 1, sample).astype(np.int64)
+        ip = np.concatenate([[0], np.cumsum(np.diff(L.indptr)[rows])]).astype(np.int64)
+        ix = np.concatenate([L.indices[L.indptr[r]:L.indptr[r + 1]] for r in rows]).astype(np.int64)
         t0 = time.time()
-        O.aggregate(ip, ix, x, pre=pre, post=pre[:sample])
-        dt = time.time() - t0
-        spent += dt
-        t_epoch += dt * (n / sample)
-        if spent > seconds_budget:
-            break
-    return {"value": 1.0 / t_epoch, "unit": "epochs/s", "cores": 1, "kind": "port",
-            "sample": f"oracle_aggregate (C, 1 thread) over {sample} of {n} destination rows x 5 passes, "
+        for F in passes:
+            O.aggregate(ip, ix, xs[F], pre=pre, post=pre[:sample])
+        return time.time() - t0
+
+    probe = max(1, min(n, 4096))
+    t_probe = run(probe)
+    sample = int(max(probe, min(n, probe * seconds_budget / max(t_probe, 1e-6))))
+    dt = run(sample) if sample > probe else t_probe
+    t_epoch = dt * (n / sample)
+    return {"value": 1.0 / t_epoch, "unit": "epochs/s", "cores": 1, "kind": "port", "seconds": dt,
+            "sample": f"oracle_aggregate (C, 1 thread) over {sample} of {n} destination rows x 5 passes ({dt:.1f} s), "
                       f"extrapolated by rows; aggregation only (no exchange at N=1, no dense GEMM)"}
 
 
