@@ -81,6 +81,8 @@ SYMBOLS = {
     "adaqp_spmm_csr_seg_f32": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, i64, i64, c_void_p,
                                          i64, c_void_p, c_void_p, C.c_int, C.c_int, C.c_int, i64, i64, i32,
                                          c_void_p, i64, c_void_p]),
+    "adaqp_gemm_tf32x3_supported": (C.c_int, [i64, i32, i32, i64, i64, i64]),
+    "adaqp_gemm_tf32x3_f32": (C.c_int, [c_void_p, i64, c_void_p, c_void_p, i64, c_void_p, i64, i32, i32, c_void_p, i64, c_void_p]),
     "adaqp_gather_rows_f32": (C.c_int, [c_void_p, i64, c_void_p, i64, i32, c_void_p, i64,
                                         c_void_p]),
 }

@@ -1,6 +1,7 @@
 """DistGCN: aggregate-then-transform GCN layers over the distributed aggregation op
-(reference: AdaQP/model/distGCN.py:9-85).  Dense GEMM, LayerNorm, dropout and ReLU stay
-torch ops (cuBLAS fp32) -- SURVEY.md row a18, not part of the hot path."""
+(reference: AdaQP/model/distGCN.py:9-85).  The dense feature x weight product runs on the
+tcgen05 tensor cores through adaqp_b200.dense (3xTF32, fp32 result; torch.matmul where the kernel does not apply
+or with ADAQP_GEMM=0); LayerNorm, dropout and ReLU stay torch ops."""
 from __future__ import annotations
 
 from typing import Any
@@ -12,6 +13,7 @@ from torch import Tensor
 from torch.nn import init
 from torch.nn.parameter import Parameter
 
+from .. import dense
 from .ops import DistAggConv
 
 
@@ -32,8 +34,8 @@ class DistGCNConv(nn.Module):
     def forward(self, feats: Tensor, graph, layer: int) -> Tensor:
         rst = DistAggConv.apply(feats, graph, layer, self.training)     # exchange + aggregation
         if self.weight is not None:
-            rst = torch.matmul(rst, self.weight)
-        if self.bias is not None:
+            rst = dense.linear(rst, self.weight, self.bias)       # rst @ W + b (distGCN.py:45-47)
+        elif self.bias is not None:
             rst = rst + self.bias
         return self._activation(rst) if self._activation is not None else rst
 

@@ -225,6 +225,17 @@ int adaqp_spmm_csr_seg_f32(const int64_t *indptr, const int64_t *seg_start, cons
                            int mean, int add_self, int accumulate, int64_t row_begin,
                            int64_t row_end, int32_t F, float *out, int64_t ldo, void *stream);
 
+/* --------------------------------------------------------------- dense GEMM
+ * C[M, N] = A[M, K] . Bt[N, K]^T (+ bias[N]) in fp32 on the tcgen05 tensor cores by 3xTF32 error-compensated
+ * splitting (csrc/gemm.cu): replaces torch.matmul(rst, self.weight) (AdaQP/model/distGCN.py:45) and the Linear
+ * layers of distSAGE.py:51-53 for tall-skinny shapes (M = inner nodes, N <= 256).  Bt_hi / Bt_lo are the
+ * transposed weight split as b_hi = b & 0xFFFFE000, b_lo = b - b_hi (host mirror: adaqp_b200/dense.py).
+ * lda / ldb multiples of 4 floats, 16-byte aligned bases; adaqp_gemm_tf32x3_supported tells whether a shape
+ * qualifies (otherwise the caller keeps torch.matmul). */
+int adaqp_gemm_tf32x3_supported(int64_t M, int32_t N, int32_t K, int64_t lda, int64_t ldb, int64_t ldc);
+int adaqp_gemm_tf32x3_f32(const float *A, int64_t lda, const float *Bt_hi, const float *Bt_lo, int64_t ldb,
+                          const float *bias, int64_t M, int32_t N, int32_t K, float *C, int64_t ldc, void *stream);
+
 /* Row gather out[i] = x[idx[i]] (copy-buffer fills of ops.py:159-164; API parity only). */
 int adaqp_gather_rows_f32(const float *x, int64_t ld, const int64_t *idx, int64_t n,
                           int32_t F, float *out, int64_t ldo, void *stream);

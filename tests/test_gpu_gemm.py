@@ -1,0 +1,62 @@
+"""tcgen05 3xTF32 GEMM (csrc/gemm.cu) vs a float64 torch reference and vs torch's fp32 matmul.
+
+Tolerance: per product the split drops a_lo*b_lo (<= 2^-22 |ab|) and truncates the lo halves to tf32
+(<= 2^-22 |ab| each), so |err| <= ~1e-6 * sum|a||b| per output; asserted at 2e-6 relative to the
+row-wise L1 mass (torch's own fp32 SIMT GEMM measures ~1e-7 on the same inputs; a plain 1xTF32 GEMM
+~5e-4, which the test also checks we are far below)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dense():
+    from adaqp_b200 import build
+    build.build()
+    from adaqp_b200 import dense as d
+    return d
+
+
+@pytest.mark.parametrize("M,K,N", [(128, 32, 16), (1000, 256, 256), (4099, 100, 256), (333, 256, 47), (257, 200, 256),
+                                   (70001, 256, 256), (5, 8, 8), (129, 300, 100)])
+def test_matches_float64(dense, M, K, N):
+    torch.manual_seed(M + K + N)
+    dev = torch.device("cuda:0")
+    x = torch.randn(M, K, device=dev)
+    x[::7] *= 100.0
+    w = torch.randn(N, K, device=dev) * 0.1
+    b = torch.randn(N, device=dev)
+    assert dense.supported(x, N, K)
+    got = dense.gemm_nt(x, w, b)
+    want = (x.double() @ w.double().t() + b.double())
+    mass = (x.double().abs() @ w.double().abs().t()) + b.double().abs()
+    err = ((got.double() - want).abs() / mass).max().item()
+    ref32 = ((x @ w.t() + b).double() - want).abs().div(mass).max().item()
+    assert err <= 2e-6, (err, ref32)
+    got2 = dense.gemm_nt(x, w)
+    assert torch.equal(got2 + b, got) or ((got2 + b) - got).abs().max() <= 1e-5 * got.abs().max()
+
+
+def test_autograd_and_fallbacks(dense):
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    x = torch.randn(3000, 256, device=dev, requires_grad=True)
+    w = (torch.randn(256, 128, device=dev) * 0.1).requires_grad_()
+    b = torch.zeros(128, device=dev, requires_grad=True)
+    y = dense.linear(x, w, b)
+    y.square().sum().backward()
+    x2, w2, b2 = (t.detach().double().requires_grad_() for t in (x, w, b))
+    (x2 @ w2 + b2).square().sum().backward()
+    for g, g2 in ((x.grad, x2.grad), (w.grad, w2.grad), (b.grad, b2.grad)):
+        assert ((g.double() - g2).abs().max() / g2.abs().max()).item() < 1e-5
+    # nn.Linear storage
+    lin = torch.nn.Linear(256, 64, bias=False).to(dev)
+    y = dense.linear_nk(x.detach(), lin.weight)
+    assert ((y.double() - x.detach().double() @ lin.weight.double().t()).abs().max() / y.abs().max()).item() < 1e-5
+    # shapes the kernel refuses fall back to torch.matmul (F = 602: 8-byte row pitch; strided views)
+    x3 = torch.randn(100, 602, device=dev)
+    assert not dense.supported(x3, 256, 602)
+    w3 = torch.randn(602, 256, device=dev)
+    assert torch.equal(dense.linear(x3, w3), torch.matmul(x3, w3))
