@@ -83,6 +83,9 @@ SYMBOLS = {
                                          c_void_p, i64, c_void_p]),
     "adaqp_gemm_tf32x3_supported": (C.c_int, [i64, i32, i32, i64, i64, i64]),
     "adaqp_gemm_tf32x3_f32": (C.c_int, [c_void_p, i64, c_void_p, c_void_p, i64, c_void_p, i64, i32, i32, c_void_p, i64, c_void_p]),
+    "adaqp_wgrad_tf32x3_supported": (C.c_int, [i64, i32, i32, i64, i64]),
+    "adaqp_wgrad_tf32x3_grid": (C.c_int, [i64]),
+    "adaqp_wgrad_tf32x3_f32": (C.c_int, [c_void_p, i64, c_void_p, i64, i64, i32, i32, c_void_p, i32, c_void_p]),
     "adaqp_gather_rows_f32": (C.c_int, [c_void_p, i64, c_void_p, i64, i32, c_void_p, i64,
                                         c_void_p]),
 }

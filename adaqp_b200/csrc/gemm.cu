@@ -276,6 +276,182 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Weight gradient: dW[N, K] = dY[M, N]^T . X[M, K], the reduction running over the M node rows (split-K).
+//
+// Both operands have the reduction index as their SLOW memory dimension (row-major [rows, features]), i.e. they are
+// MN-major for the tensor core.  A TMA box {32 features, 16 rows} with SWIZZLE_128B lands exactly as the canonical
+// MN-major SWIZZLE_128B atoms (128-byte feature runs, 8 rows = one 1024-byte atom): per 32-feature chunk one box,
+// chunks LBO = 2048 bytes apart, the two 8-row groups of a box SBO = 1024 bytes apart; one tcgen05.mma (K = 8 rows)
+// reads one atom per chunk.  Every CTA reduces a contiguous range of 16-row blocks into TWO fp32 accumulators in
+// TMEM (output features 0-127 and 128-255: all 512 columns) with the same 3xTF32 splitting as above -- here both
+// operand tiles are split by 8 warps -- and writes its partial [N, K] to `partials[cta]`; the host mirror sums the
+// partials (deterministic for a fixed grid).
+constexpr int kWgThreads = 512;               // 16 warps
+constexpr int kWgRows = 16;                   // rows (MMA K) per stage = 2 MMA K steps
+constexpr int kWgStages = 3;
+constexpr uint32_t kWgBox = kWgRows * 128;    // bytes of one {32 features x 16 rows} box
+constexpr uint32_t kWgOperand = 8 * kWgBox;   // up to 256 features = 8 boxes = 16 KB
+constexpr uint32_t kWgStageBytes = 4 * kWgOperand;   // dY_hi | dY_lo | X_hi | X_lo = 64 KB
+constexpr uint32_t kWgSmemBytes = kWgStages * kWgStageBytes + 1024 + 256;
+
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)(kWgBox >> 4) << 16;              // leading byte offset: next 32-feature chunk
+    d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset: next 8-row group
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
+                    float *__restrict__ partials, int M, int N, int K) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_addr(smem_raw) + 1023u) & ~1023u;
+    uint8_t *gen = smem_raw + (base - smem_addr(smem_raw));
+    const uint32_t bars = base + kWgStages * kWgStageBytes;
+    auto bar_full = [&](int s) { return bars + 8u * s; };
+    auto bar_split = [&](int s) { return bars + 8u * (kWgStages + s); };
+    auto bar_empty = [&](int s) { return bars + 8u * (2 * kWgStages + s); };
+    const uint32_t bar_acc = bars + 8u * (3 * kWgStages);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gen + kWgStages * kWgStageBytes + 8 * (3 * kWgStages + 1));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_chunks = (N + 31) / 32, k_chunks = (K + 31) / 32;      // 32-feature boxes of dY / X
+    const int m_tiles = (N + 127) / 128;                               // accumulators (MMA M = 128 output features)
+    const int n_mma = ((K + 15) / 16) * 16;                            // MMA N = input features
+    const int blocks = (M + kWgRows - 1) / kWgRows;
+    const int per = (blocks + gridDim.x - 1) / gridDim.x;
+    const int b0 = blockIdx.x * per;
+    const int b1 = (b0 + per < blocks) ? b0 + per : blocks;
+    const uint32_t stage_tx = (uint32_t)(n_chunks + k_chunks) * kWgBox;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kWgStages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_split(s), 8); mbar_init(bar_empty(s), 1); }
+        mbar_init(bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(tmem_slot)), "n"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int b = b0; b < b1; ++b) {
+                mbar_wait(bar_empty(s), ph ^ 1u);
+                const uint32_t st = base + s * kWgStageBytes;
+                mbar_expect_tx(bar_full(s), stage_tx);
+                for (int c = 0; c < n_chunks; ++c) tma_load_2d(st + c * kWgBox, &map_dy, c * 32, b * kWgRows, bar_full(s));
+                for (int c = 0; c < k_chunks; ++c) tma_load_2d(st + 2 * kWgOperand + c * kWgBox, &map_x, c * 32, b * kWgRows, bar_full(s));
+                if (++s == kWgStages) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            uint32_t idesc = umma_idesc_tf32(n_mma) | (1u << 15) | (1u << 16);     // A and B MN-major
+            int s = 0; uint32_t ph = 0;
+            for (int b = b0; b < b1; ++b) {
+                mbar_wait(bar_full(s), ph);
+                mbar_wait(bar_split(s), ph);
+                tcgen05_fence_after();
+                const uint32_t st = base + s * kWgStageBytes;
+#pragma unroll
+                for (int k = 0; k < kWgRows / 8; ++k) {
+                    const uint64_t xhi = umma_desc_mn_sw128(st + 2 * kWgOperand + k * 1024);
+                    const uint64_t xlo = umma_desc_mn_sw128(st + 3 * kWgOperand + k * 1024);
+                    for (int mt = 0; mt < m_tiles; ++mt) {
+                        const uint64_t yhi = umma_desc_mn_sw128(st + mt * 4 * kWgBox + k * 1024);
+                        const uint64_t ylo = umma_desc_mn_sw128(st + kWgOperand + mt * 4 * kWgBox + k * 1024);
+                        const uint32_t d = tmem_base + (uint32_t)mt * kMaxN;
+                        umma_tf32(d, ylo, xhi, idesc, (b != b0) || (k != 0));
+                        umma_tf32(d, yhi, xlo, idesc, 1);
+                        umma_tf32(d, yhi, xhi, idesc, 1);
+                    }
+                }
+                tcgen05_commit(bar_empty(s));
+                if (++s == kWgStages) { s = 0; ph ^= 1u; }
+            }
+            tcgen05_commit(bar_acc);
+        }
+    } else if (warp >= 8) {
+        // split both operand tiles: hi in place, lo into the second buffer (same swizzled offsets)
+        const int tid = threadIdx.x - 256;                       // 0..255
+        int s = 0; uint32_t ph = 0;
+        const int y_vec = n_chunks * (int)(kWgBox / 16), x_vec = k_chunks * (int)(kWgBox / 16);
+        for (int b = b0; b < b1; ++b) {
+            mbar_wait(bar_full(s), ph);
+            uint8_t *st = gen + s * kWgStageBytes;
+            for (int part = 0; part < 2; ++part) {
+                float4 *hi = reinterpret_cast<float4 *>(st + part * 2 * kWgOperand);
+                float4 *lo = reinterpret_cast<float4 *>(st + part * 2 * kWgOperand + kWgOperand);
+                const int nvec = part == 0 ? y_vec : x_vec;
+                for (int idx = tid; idx < nvec; idx += 256) {
+                    float4 v = hi[idx];
+                    float4 h, l;
+                    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+                    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+                    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+                    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+                    hi[idx] = h;
+                    lo[idx] = l;
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_split(s));
+            if (++s == kWgStages) { s = 0; ph ^= 1u; }
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3;
+        float *out = partials + (size_t)blockIdx.x * N * K;
+        if (b1 > b0) {
+            mbar_wait(bar_acc, 0);
+            tcgen05_fence_after();
+        }
+        for (int mt = 0; mt < m_tiles; ++mt) {
+            const int row = mt * 128 + q * 32 + lane;            // output feature n
+            for (int c0 = 0; c0 < n_mma; c0 += 32) {
+                uint32_t r[32];
+                if (b1 > b0) {
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * kMaxN + c0);
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                        : "r"(taddr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = 0u;      // a CTA without rows contributes zeros
+                }
+                if (row < N) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (c0 + j < K) out[(size_t)row * K + c0 + j] = __uint_as_float(r[j]);
+                }
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -289,6 +465,7 @@ EncodeTiledFn encoder() {
 
 // 2-D fp32 map {cols, rows} (cols contiguous), box {32, box_rows}, SWIZZLE_128B, out-of-bounds elements read as zero
 int make_tile_map(CUtensorMap *m, const float *base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    // box = {32 columns (one 128-byte swizzle row), box_rows}
     EncodeTiledFn enc = encoder();
     ADAQP_REQUIRE(enc != nullptr, ADAQP_EINVAL, "cuTensorMapEncodeTiled not available from the driver");
     const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -334,6 +511,35 @@ int adaqp_gemm_tf32x3_f32(const float *A, int64_t lda, const float *Bt_hi, const
     ADAQP_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     gemm_tf32x3_kernel<<<grid, kGemmThreads, kSmemBytes, (cudaStream_t)stream>>>(ma, mh, ml, bias, C, ldc, (int)M, N, K);
     return adaqp_check_launch("gemm_tf32x3_kernel");
+}
+
+int adaqp_wgrad_tf32x3_supported(int64_t M, int32_t N, int32_t K, int64_t ldy, int64_t ldx) {
+    if (M <= 0 || N <= 0 || K <= 0 || N > kMaxN || K > kMaxN || M >= (1ll << 31)) return 0;
+    if ((ldy & 3) || (ldx & 3) || ldy < N || ldx < K) return 0;
+    return 1;
+}
+
+int adaqp_wgrad_tf32x3_grid(int64_t M) {
+    const int sms = adaqp_sm_count() > 0 ? adaqp_sm_count() : 148;
+    const int64_t blocks = (M + kWgRows - 1) / kWgRows;
+    return (int)(blocks < sms ? (blocks < 1 ? 1 : blocks) : sms);
+}
+
+int adaqp_wgrad_tf32x3_f32(const float *dY, int64_t ldy, const float *X, int64_t ldx, int64_t M, int32_t N, int32_t K,
+                           float *partials, int32_t grid, void *stream) {
+    ADAQP_REQUIRE(adaqp_wgrad_tf32x3_supported(M, N, K, ldy, ldx), ADAQP_ELIMIT,
+                  "adaqp_wgrad_tf32x3_f32: unsupported shape M=%lld N=%d K=%d", (long long)M, N, K);
+    ADAQP_REQUIRE(dY && X && partials, ADAQP_EINVAL, "adaqp_wgrad_tf32x3_f32: null pointer");
+    ADAQP_REQUIRE(((uintptr_t)dY & 15) == 0 && ((uintptr_t)X & 15) == 0, ADAQP_EALIGN, "adaqp_wgrad_tf32x3_f32: 16-byte alignment");
+    ADAQP_REQUIRE(grid == adaqp_wgrad_tf32x3_grid(M), ADAQP_EINVAL, "adaqp_wgrad_tf32x3_f32: partials must hold adaqp_wgrad_tf32x3_grid(M) slices");
+    CUtensorMap my, mx;
+    int rc = make_tile_map(&my, dY, M, N, ldy, kWgRows);
+    if (rc) return rc;
+    rc = make_tile_map(&mx, X, M, K, ldx, kWgRows);
+    if (rc) return rc;
+    ADAQP_CUDA(cudaFuncSetAttribute(wgrad_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmemBytes));
+    wgrad_tf32x3_kernel<<<grid, kWgThreads, kWgSmemBytes, (cudaStream_t)stream>>>(my, mx, partials, (int)M, N, K);
+    return adaqp_check_launch("wgrad_tf32x3_kernel");
 }
 
 }  // extern "C"

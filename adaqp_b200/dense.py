@@ -6,8 +6,9 @@ Host mirror of `adaqp_gemm_tf32x3_f32` (csrc/gemm.cu): `linear(x, weight, bias)`
 (DistSAGEConv, distSAGE.py:51-53).  fp32 in / out; the tensor cores run three tf32 products of
 error-compensated operand halves (a = a_hi + a_lo, a_hi = a & 0xFFFFE000), accumulated in fp32.
 
-Backward: dX = dY @ W^T runs through the same kernel; dW = X^T @ dY (reduction over the node
-dimension, MN-major operands) and the bias gradient stay torch ops.
+Backward: dX = dY @ W^T runs through the same kernel; dW = dY^T @ X (reduction over the node
+dimension) through the split-K kernel `adaqp_wgrad_tf32x3_f32`, which reads both operands
+MN-major straight from their row-major storage; the bias gradient stays a torch reduction.
 
 Shapes the kernel does not take (row pitch not a multiple of 16 bytes, N > 256, CPU tensors) and
 `ADAQP_GEMM=0` use torch.matmul, the reference's own arithmetic.
@@ -71,6 +72,29 @@ def gemm_nt(x: Tensor, bt: Tensor, bias: Tensor = None) -> Tensor:
     return out
 
 
+def wgrad_supported(dy: Tensor, x: Tensor) -> bool:
+    if not (enabled() and dy.is_cuda and x.is_cuda and dy.dtype == x.dtype == torch.float32):
+        return False
+    if dy.dim() != 2 or x.dim() != 2 or dy.stride(1) != 1 or x.stride(1) != 1 or dy.shape[0] != x.shape[0]:
+        return False
+    if dy.data_ptr() % 16 or x.data_ptr() % 16 or dy.shape[0] == 0:
+        return False
+    return bool(_lib.load().adaqp_wgrad_tf32x3_supported(dy.shape[0], dy.shape[1], x.shape[1], dy.stride(0), x.stride(0)))
+
+
+def gemm_tn(dy: Tensor, x: Tensor) -> Tensor:
+    """dy[M, N]^T @ x[M, K] -> [N, K] (the layers' weight gradient), per-CTA partial sums added here."""
+    L = _lib.load()
+    M, N = dy.shape
+    K = x.shape[1]
+    grid = L.adaqp_wgrad_tf32x3_grid(M)
+    partials = torch.empty((grid, N, K), dtype=torch.float32, device=dy.device)
+    rc = L.adaqp_wgrad_tf32x3_f32(dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), M, N, K, partials.data_ptr(), grid,
+                                  _lib.stream_ptr())
+    _lib.check(rc, "adaqp_wgrad_tf32x3_f32")
+    return partials.sum(0)
+
+
 class _LinearNK(Function):
     """y = x @ w_nk^T + b with w_nk stored [N, K]."""
 
@@ -90,7 +114,7 @@ class _LinearNK(Function):
             wt = w_nk.t().contiguous()
             dx = gemm_nt(dy, wt) if supported(dy, wt.shape[0], wt.shape[1]) else dy @ w_nk
         if ctx.needs_input_grad[1]:
-            dw = dy.t() @ x
+            dw = gemm_tn(dy, x) if wgrad_supported(dy, x) else dy.t() @ x
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy.sum(0)
         return dx, dw, db

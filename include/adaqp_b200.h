@@ -236,6 +236,14 @@ int adaqp_gemm_tf32x3_supported(int64_t M, int32_t N, int32_t K, int64_t lda, in
 int adaqp_gemm_tf32x3_f32(const float *A, int64_t lda, const float *Bt_hi, const float *Bt_lo, int64_t ldb,
                           const float *bias, int64_t M, int32_t N, int32_t K, float *C, int64_t ldc, void *stream);
 
+/* Weight gradient dW[N, K] = dY[M, N]^T . X[M, K] (the `X^T . dY` of the layers' backward), split over the M node rows:
+ * CTA c writes its partial sum to partials[c] ([grid, N, K] fp32, grid = adaqp_wgrad_tf32x3_grid(M)); the caller adds the
+ * slices.  Same 3xTF32 arithmetic; both operands are read MN-major straight from their row-major storage. */
+int adaqp_wgrad_tf32x3_supported(int64_t M, int32_t N, int32_t K, int64_t ldy, int64_t ldx);
+int adaqp_wgrad_tf32x3_grid(int64_t M);
+int adaqp_wgrad_tf32x3_f32(const float *dY, int64_t ldy, const float *X, int64_t ldx, int64_t M, int32_t N, int32_t K,
+                           float *partials, int32_t grid, void *stream);
+
 /* Row gather out[i] = x[idx[i]] (copy-buffer fills of ops.py:159-164; API parity only). */
 int adaqp_gather_rows_f32(const float *x, int64_t ld, const int64_t *idx, int64_t n,
                           int32_t F, float *out, int64_t ldo, void *stream);

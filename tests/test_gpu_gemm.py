@@ -60,3 +60,28 @@ def test_autograd_and_fallbacks(dense):
     assert not dense.supported(x3, 256, 602)
     w3 = torch.randn(602, 256, device=dev)
     assert torch.equal(dense.linear(x3, w3), torch.matmul(x3, w3))
+
+
+@pytest.mark.parametrize("M,N,K", [(16, 128, 32), (1000, 256, 256), (4099, 256, 100), (70001, 256, 256), (333, 128, 200),
+                                   (50, 64, 256), (7, 256, 8), (3000, 100, 256)])
+def test_weight_gradient_split_k(dense, M, N, K):
+    """dW = dY^T X on the tensor cores (MN-major operands, split over the rows) vs float64."""
+    torch.manual_seed(M + N + K)
+    dev = torch.device("cuda:0")
+    dy = torch.randn(M, N, device=dev) * 1e-3
+    dy[::5] = 0.0                                 # all-zero gradient rows (non-training nodes)
+    x = torch.relu(torch.randn(M, K, device=dev))
+    assert dense.wgrad_supported(dy, x)
+    got = dense.gemm_tn(dy, x)
+    want = dy.double().t() @ x.double()
+    mass = dy.double().abs().t() @ x.double().abs()
+    err = ((got.double() - want).abs() / (mass + 1e-30)).max().item()
+    assert got.shape == (N, K) and err <= 2e-6, err
+    again = dense.gemm_tn(dy, x)
+    assert torch.equal(got, again), "deterministic for a fixed grid"
+
+
+def test_wgrad_fallback_shapes(dense):
+    dev = torch.device("cuda:0")
+    assert not dense.wgrad_supported(torch.randn(100, 47, device=dev), torch.randn(100, 256, device=dev))   # 188-byte pitch
+    assert not dense.wgrad_supported(torch.randn(100, 256, device=dev), torch.randn(100, 602, device=dev))  # K > 256
