@@ -24,6 +24,7 @@ from torch.autograd import Function
 from . import _lib
 
 _ENABLED = None
+LAUNCHES = {"gemm_tf32x3_kernel": 0, "wgrad_tf32x3_kernel": 0}     # launch counters (bench.py: gpu_launches)
 
 
 def enabled() -> bool:
@@ -69,6 +70,7 @@ def gemm_nt(x: Tensor, bt: Tensor, bias: Tensor = None) -> Tensor:
                                            bias.data_ptr() if bias is not None else None, M, N, K, out.data_ptr(),
                                            out.stride(0), _lib.stream_ptr())
     _lib.check(rc, "adaqp_gemm_tf32x3_f32")
+    LAUNCHES["gemm_tf32x3_kernel"] += 1
     return out
 
 
@@ -92,6 +94,7 @@ def gemm_tn(dy: Tensor, x: Tensor) -> Tensor:
     rc = L.adaqp_wgrad_tf32x3_f32(dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), M, N, K, partials.data_ptr(), grid,
                                   _lib.stream_ptr())
     _lib.check(rc, "adaqp_wgrad_tf32x3_f32")
+    LAUNCHES["wgrad_tf32x3_kernel"] += 1
     return partials.sum(0)
 
 

@@ -298,7 +298,10 @@ def run_ours(args, rank, world):
     p2p = comm.ctx.comm_buffer.p2p
     if p2p is not None:
         p2p.profile = True
+    from adaqp_b200 import dense
+    gemm_before = dict(dense.LAUNCHES)
     ms, traced_all = timed(args.steps, dev_step)
+    gemm_launches = {k: dense.LAUNCHES[k] - gemm_before[k] for k in dense.LAUNCHES}
     exch_times = None
     if p2p is not None:
         exch_times = p2p.kernel_times_ms()
@@ -359,7 +362,7 @@ def run_ours(args, rank, world):
     # segment -- unless ADAQP_MARGINAL_SPLIT=0) + per exchange: send, flag wait, receive (quant) or
     # send, flag wait, ack (fp32)
     split_extra = 5 if (eng.use_parallel and eng.num_marginal > 0 and os.environ.get("ADAQP_MARGINAL_SPLIT", "1") != "0") else 0
-    launches_per_epoch = launches + split_extra + n_exch * 3
+    launches_per_epoch = launches + split_extra + n_exch * 3 + sum(gemm_launches.values()) // max(args.steps, 1)
     out = {
         "metric": "epochs_per_sec", "value": args.steps / (ms / 1e3), "unit": "epochs/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
@@ -379,6 +382,8 @@ def run_ours(args, rank, world):
                      "algorithmic_bytes_per_epoch": alg_bytes, "launches_per_epoch": launches, "spmm_ms_per_epoch": agg_ms,
                      "gather_bound": {"note": "no-reuse bound 4*F*nnz: what a random gather must move when the source matrix exceeds L2",
                                       "achieved_GBps": sum(4 * F * int(eng.layout.indptr[-1]) for F in [dims[0], dims[1], dims[2], dims[2], dims[1]]) / (agg_ms * 1e-3) / 1e9}},
+        "dense_gemm": {"kernels_per_epoch": {k: v // max(args.steps, 1) for k, v in gemm_launches.items()},
+                       "arithmetic": "tcgen05 kind::tf32 x3 (error-compensated split, fp32 accumulate)" if dense.enabled() else "torch.matmul fp32"},
         "final_loss": losses[-1],
         "exchange": exchange_stats(comm.ctx.comm_buffer.p2p, eng, traced_all) if world > 1 else None,
         "roofline_exchange": exchange_roofline(comm.ctx.comm_buffer.p2p, eng, exch_times, args.steps, peaks["hbm_gbs"]) if world > 1 else None,
