@@ -280,10 +280,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 // Weight gradient: dW[N, K] = dY[M, N]^T . X[M, K], the reduction running over the M node rows (split-K).
 //
 // Both operands have the reduction index as their SLOW memory dimension (row-major [rows, features]), i.e. they are
-// MN-major for the tensor core.  A TMA box {32 features, 16 rows} with SWIZZLE_128B lands exactly as the canonical
-// MN-major SWIZZLE_128B atoms (128-byte feature runs, 8 rows = one 1024-byte atom): per 32-feature chunk one box,
-// chunks LBO = 2048 bytes apart, the two 8-row groups of a box SBO = 1024 bytes apart; one tcgen05.mma (K = 8 rows)
-// reads one atom per chunk.  Every CTA reduces a contiguous range of 16-row blocks into TWO fp32 accumulators in
+// MN-major for the tensor core.  For 32-bit MN-major operands the only swizzled shared-memory layout tcgen05 accepts is
+// SWIZZLE_128B_BASE32B (32-byte chunks permuted inside 128-byte feature runs, atoms of 4 rows = 512 bytes; CUTLASS:
+// "for mn-major tf32 operands, SW128_32B is the only available smem layout"), which is exactly what a TMA box
+// {32 features, 16 rows} with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B lands: per 32-feature chunk one box, chunks
+// LBO = 2048 bytes apart, 4-row groups SBO = 512 bytes apart; one tcgen05.mma (K = 8 rows) reads two atoms per chunk.  Every CTA reduces a contiguous range of 16-row blocks into TWO fp32 accumulators in
 // TMEM (output features 0-127 and 128-255: all 512 columns) with the same 3xTF32 splitting as above -- here both
 // operand tiles are split by 8 warps -- and writes its partial [N, K] to `partials[cta]`; the host mirror sums the
 // partials (deterministic for a fixed grid).
@@ -299,9 +300,9 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);
     d |= (uint64_t)(kWgBox >> 4) << 16;              // leading byte offset: next 32-feature chunk
-    d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset: next 8-row group
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)(512 >> 4) << 32;                 // stride byte offset: next 4-row group
+    d |= (uint64_t)1 << 46;                          // version
+    d |= (uint64_t)1 << 61;                          // SWIZZLE_128B_BASE32B
     return d;
 }
 
@@ -464,7 +465,8 @@ EncodeTiledFn encoder() {
 }
 
 // 2-D fp32 map {cols, rows} (cols contiguous), box {32, box_rows}, SWIZZLE_128B, out-of-bounds elements read as zero
-int make_tile_map(CUtensorMap *m, const float *base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+int make_tile_map(CUtensorMap *m, const float *base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                  CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     // box = {32 columns (one 128-byte swizzle row), box_rows}
     EncodeTiledFn enc = encoder();
     ADAQP_REQUIRE(enc != nullptr, ADAQP_EINVAL, "cuTensorMapEncodeTiled not available from the driver");
@@ -473,7 +475,7 @@ int make_tile_map(CUtensorMap *m, const float *base, int64_t rows, int64_t cols,
     const cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                           swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     ADAQP_REQUIRE(r == CUDA_SUCCESS, ADAQP_EINVAL, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     return 0;
 }
@@ -533,9 +535,9 @@ int adaqp_wgrad_tf32x3_f32(const float *dY, int64_t ldy, const float *X, int64_t
     ADAQP_REQUIRE(((uintptr_t)dY & 15) == 0 && ((uintptr_t)X & 15) == 0, ADAQP_EALIGN, "adaqp_wgrad_tf32x3_f32: 16-byte alignment");
     ADAQP_REQUIRE(grid == adaqp_wgrad_tf32x3_grid(M), ADAQP_EINVAL, "adaqp_wgrad_tf32x3_f32: partials must hold adaqp_wgrad_tf32x3_grid(M) slices");
     CUtensorMap my, mx;
-    int rc = make_tile_map(&my, dY, M, N, ldy, kWgRows);
+    int rc = make_tile_map(&my, dY, M, N, ldy, kWgRows, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
-    rc = make_tile_map(&mx, X, M, K, ldx, kWgRows);
+    rc = make_tile_map(&mx, X, M, K, ldx, kWgRows, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
     ADAQP_CUDA(cudaFuncSetAttribute(wgrad_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmemBytes));
     wgrad_tf32x3_kernel<<<grid, kWgThreads, kWgSmemBytes, (cudaStream_t)stream>>>(my, mx, partials, (int)M, N, K);
