@@ -26,7 +26,6 @@ namespace {
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 constexpr int kUnroll = 4;
-constexpr int kRowsPerGrab = 4;
 
 // hint bits (option "spmm_hints"): the output rows and the index stream are touched once per launch,
 // the gathered source rows are what should stay in L2
@@ -91,8 +90,8 @@ spmm_csr_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ 
 #pragma unroll
     for (int c = 0; c < CHUNKS; ++c) colok[c] = ((c * 32 + lane) * VEC) < F;
 
-    // Frontier scheduling: warps take the next kRowsPerGrab destination rows from a global
-    // counter, so the rows in flight are always one contiguous window (~ #warps * kRowsPerGrab
+    // Frontier scheduling: warps take the next `rows_per_grab` destination rows from a global
+    // counter, so the rows in flight are always one contiguous window (~ #warps * rows_per_grab
     // rows) however uneven the degrees are.  With a static row -> warp map the warps drift
     // apart (power-law degrees) and the set of source rows being reused grows far beyond
     // L2: ncu showed a 14 % L2 hit rate on a graph where 60 % of the edges stay inside 4 MB
