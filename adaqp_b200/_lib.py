@@ -59,6 +59,8 @@ SYMBOLS = {
                                  c_void_p, c_void_p]),
     "adaqp_unpack_f32": (C.c_int, [c_void_p, c_void_p, c_void_p, i64, i64, C.c_int, c_void_p,
                                    c_void_p]),
+    "adaqp_pack_f16": (C.c_int, [c_void_p, c_void_p, c_void_p, i64, i64, C.c_int, u64, u64, c_void_p, c_void_p]),
+    "adaqp_unpack_f16": (C.c_int, [c_void_p, c_void_p, c_void_p, i64, i64, C.c_int, c_void_p, c_void_p]),
     "adaqp_row_minmax_f32": (C.c_int, [c_void_p, i64, i64, C.c_int, c_void_p, c_void_p, c_void_p,
                                        c_void_p]),
     "adaqp_slab_alloc": (C.c_int, [C.POINTER(c_void_p), C.c_size_t]),

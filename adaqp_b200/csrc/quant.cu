@@ -8,6 +8,8 @@
 // Philox block per byte, loads coalesced along d.  HBM-bound for bits <= 4; for 8-bit
 // the mandated per-byte Philox (parity with curand_init(seed, k, offset)) makes it
 // integer-ALU bound.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace {
@@ -99,6 +101,58 @@ unpack_flat_kernel(const uint8_t *__restrict__ packed, const float *__restrict__
                 }
             }
             if (++d == F) { d = 0; ++no; }
+        }
+    }
+}
+
+// ---- fp16 instantiation of the reference's dispatch (AT_DISPATCH_FLOATING_TYPES_AND_HALF, .cu:81,138; admitted by
+// check.h:22-27).  scalar_t = c10::Half evaluates every Half (op) Half in float and rounds back to half, and
+// Half + float in float (c10/util/Half-inl.h):
+//   t1 = half(float(x) - float(min)); t2 = half(float(t1) * float(scale)); f = float(t2) + noise;
+//   q = float2int_rn(fmax(f - 0.5, 0))     (t2 <= 65504: the fp32 subtraction equals the reference's double one)
+// Not on the hot path (every boundary message is fp32): one packed byte per thread, no vector paths.
+template <int BITS>
+__global__ void __launch_bounds__(kPackThreads)
+pack_flat_half_kernel(const __half *__restrict__ data, const __half *__restrict__ mn, const __half *__restrict__ scale,
+                      int64_t N, int64_t F, int64_t total, uint64_t seed, uint64_t offset, uint8_t *__restrict__ packed) {
+    constexpr int WPT = 8 / BITS;
+    const int64_t k = (int64_t)blockIdx.x * kPackThreads + threadIdx.x;
+    if (k >= total) return;
+    const int64_t no = k / F, d = k - no * F;
+    float u[WPT];
+    byte_noise<WPT>(seed, (uint64_t)k, offset, u);
+    uint32_t byte = 0;
+#pragma unroll
+    for (int ni = 0; ni < WPT; ++ni) {
+        const int64_t n = no * WPT + ni;
+        if (n < N) {
+            const __half t1 = __float2half_rn(__fsub_rn(__half2float(data[n * F + d]), __half2float(mn[n])));
+            const __half t2 = __float2half_rn(__fmul_rn(__half2float(t1), __half2float(scale[n])));
+            const float f = __fadd_rn(__half2float(t2), u[ni]);
+            const int q = __float2int_rn(fmaxf(__fsub_rn(f, 0.5f), 0.0f));      // inf -> INT_MAX, NaN -> 0 as in the reference
+            byte |= ((uint32_t)q << (ni * BITS));
+        }
+    }
+    packed[k] = (uint8_t)byte;
+}
+
+template <int BITS>
+__global__ void __launch_bounds__(kPackThreads)
+unpack_flat_half_kernel(const uint8_t *__restrict__ packed, const __half *__restrict__ scale, const __half *__restrict__ mn,
+                        int64_t N, int64_t F, int64_t total, __half *__restrict__ out) {
+    constexpr int WPT = 8 / BITS;
+    constexpr uint32_t MASK = (1u << BITS) - 1u;
+    const int64_t k = (int64_t)blockIdx.x * kPackThreads + threadIdx.x;
+    if (k >= total) return;
+    const int64_t no = k / F, d = k - no * F;
+    const uint32_t byte = packed[k];
+#pragma unroll
+    for (int ni = 0; ni < WPT; ++ni) {
+        const int64_t n = no * WPT + ni;
+        if (n < N) {
+            const __half q = __float2half_rn((float)((byte >> (ni * BITS)) & MASK));
+            const __half dv = __float2half_rn(__fdiv_rn(__half2float(q), __half2float(scale[n])));
+            out[n * F + d] = __float2half_rn(__fadd_rn(__half2float(dv), __half2float(mn[n])));
         }
     }
 }
@@ -208,6 +262,47 @@ int adaqp_unpack_f32(const uint8_t *packed, const float *scale, const float *mn,
     }
 #undef LAUNCH_UNPACK
     return adaqp_check_launch("unpack_flat_kernel");
+}
+
+int adaqp_pack_f16(const void *data, const void *mn, const void *scale, int64_t N, int64_t F, int bits, uint64_t seed,
+                   uint64_t offset, uint8_t *packed, void *stream) {
+    ADAQP_REQUIRE(valid_bits(bits), ADAQP_EINVAL, "adaqp_pack_f16: 8 %% bits != 0 (bits=%d)", bits);
+    ADAQP_REQUIRE(N >= 0 && F >= 0, ADAQP_EINVAL, "adaqp_pack_f16: negative shape");
+    const int64_t total = adaqp_packed_nbytes(N, F, bits);
+    if (total == 0) return 0;
+    ADAQP_REQUIRE(data && mn && scale && packed, ADAQP_EINVAL, "adaqp_pack_f16: null pointer");
+    const int64_t blocks = (total + kPackThreads - 1) / kPackThreads;
+    ADAQP_REQUIRE(blocks < (1ll << 31), ADAQP_ELIMIT, "adaqp_pack_f16: too many bytes");
+    cudaStream_t s = (cudaStream_t)stream;
+    const __half *x = (const __half *)data, *m = (const __half *)mn, *sc = (const __half *)scale;
+    switch (bits) {
+        case 1: pack_flat_half_kernel<1><<<(unsigned)blocks, kPackThreads, 0, s>>>(x, m, sc, N, F, total, seed, offset, packed); break;
+        case 2: pack_flat_half_kernel<2><<<(unsigned)blocks, kPackThreads, 0, s>>>(x, m, sc, N, F, total, seed, offset, packed); break;
+        case 4: pack_flat_half_kernel<4><<<(unsigned)blocks, kPackThreads, 0, s>>>(x, m, sc, N, F, total, seed, offset, packed); break;
+        default: pack_flat_half_kernel<8><<<(unsigned)blocks, kPackThreads, 0, s>>>(x, m, sc, N, F, total, seed, offset, packed); break;
+    }
+    return adaqp_check_launch("pack_flat_half_kernel");
+}
+
+int adaqp_unpack_f16(const uint8_t *packed, const void *scale, const void *mn, int64_t N, int64_t F, int bits, void *out,
+                     void *stream) {
+    ADAQP_REQUIRE(valid_bits(bits), ADAQP_EINVAL, "adaqp_unpack_f16: 8 %% bits != 0 (bits=%d)", bits);
+    ADAQP_REQUIRE(N >= 0 && F >= 0, ADAQP_EINVAL, "adaqp_unpack_f16: negative shape");
+    const int64_t total = adaqp_packed_nbytes(N, F, bits);
+    if (total == 0) return 0;
+    ADAQP_REQUIRE(packed && scale && mn && out, ADAQP_EINVAL, "adaqp_unpack_f16: null pointer");
+    const int64_t blocks = (total + kPackThreads - 1) / kPackThreads;
+    ADAQP_REQUIRE(blocks < (1ll << 31), ADAQP_ELIMIT, "adaqp_unpack_f16: too many bytes");
+    cudaStream_t s = (cudaStream_t)stream;
+    const __half *sc = (const __half *)scale, *m = (const __half *)mn;
+    __half *o = (__half *)out;
+    switch (bits) {
+        case 1: unpack_flat_half_kernel<1><<<(unsigned)blocks, kPackThreads, 0, s>>>(packed, sc, m, N, F, total, o); break;
+        case 2: unpack_flat_half_kernel<2><<<(unsigned)blocks, kPackThreads, 0, s>>>(packed, sc, m, N, F, total, o); break;
+        case 4: unpack_flat_half_kernel<4><<<(unsigned)blocks, kPackThreads, 0, s>>>(packed, sc, m, N, F, total, o); break;
+        default: unpack_flat_half_kernel<8><<<(unsigned)blocks, kPackThreads, 0, s>>>(packed, sc, m, N, F, total, o); break;
+    }
+    return adaqp_check_launch("unpack_flat_half_kernel");
 }
 
 int adaqp_row_minmax_f32(const float *data, int64_t N, int64_t F, int bits, float *rmin,

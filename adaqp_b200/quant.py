@@ -7,8 +7,9 @@ launch and the same consumption of the default CUDA generator
 (quantization_cuda_kernel.cu:66-72: one philox_engine_inputs(F * 8/bits) per call).
 The arithmetic runs in libadaqp_b200.so through the C ABI; there is no CPU path.
 
-Only the fp32 instantiation is provided (the boundary messages on the hot path are
-fp32; the reference's fp16/fp64 dispatch is not used by its own callers).
+float32 and float16 instantiations, the two dtypes the reference's boundary check admits
+(check.h:22-27; its fp64 kernel instantiation is unreachable behind that check).  The boundary
+messages on the hot path are fp32; fp16 follows c10::Half arithmetic (csrc/quant.cu).
 """
 from __future__ import annotations
 
@@ -27,8 +28,13 @@ def _check_float_tensor(t: Tensor, name: str, ndim: int):
         raise RuntimeError(f"The dimension of {name} is not correct!")
     if t.dtype not in (torch.float32, torch.float16):
         raise RuntimeError(f"The type of {name} is not correct!")
-    if t.dtype != torch.float32:
-        raise RuntimeError(f"{name}: only the float32 instantiation is built in adaqp_b200")
+
+
+def _same_dtype(ref: Tensor, *others):
+    """The reference dispatches on one tensor's dtype and takes data_ptr<scalar_t>() of the others, which raises on a mismatch."""
+    for name, t in others:
+        if t.dtype != ref.dtype:
+            raise RuntimeError(f"expected scalar type {ref.dtype} but found {t.dtype} for {name}")
 
 
 def philox_engine_inputs(device: torch.device, increment: int):
@@ -52,6 +58,7 @@ def pack_single_precision(data: Tensor, min: Tensor, max: Tensor, scale: Tensor,
     bits = int(bits)
     if bits <= 0 or 8 % bits != 0:
         raise RuntimeError("Expected 8 % bits == 0 to be true, but got false.")
+    _same_dtype(data, ("min", min), ("scale", scale))
     L = _lib.load()
     N, F = data.shape
     with torch.cuda.device(data.device):
@@ -59,9 +66,10 @@ def pack_single_precision(data: Tensor, min: Tensor, max: Tensor, scale: Tensor,
         seed, offset = philox_engine_inputs(data.device, F * (8 // bits))
         if not stochastic:
             raise RuntimeError("Expected stochastic to be true, but got false.")
-        rc = L.adaqp_pack_f32(data.data_ptr(), min.data_ptr(), scale.data_ptr(), N, F, bits,
-                              seed, offset, packed.data_ptr(), _lib.stream_ptr())
-        _lib.check(rc, "adaqp_pack_f32")
+        fn = L.adaqp_pack_f32 if data.dtype == torch.float32 else L.adaqp_pack_f16
+        rc = fn(data.data_ptr(), min.data_ptr(), scale.data_ptr(), N, F, bits,
+                seed, offset, packed.data_ptr(), _lib.stream_ptr())
+        _lib.check(rc, "adaqp_pack")
     return packed
 
 
@@ -86,17 +94,20 @@ def unpack_single_precision(data: Tensor, bits: int, scale: Tensor, min: Tensor,
     need = L.adaqp_packed_nbytes(N, F, bits)
     if data.numel() < need:
         raise RuntimeError(f"data holds {data.numel()} bytes, {need} needed for N={N}, F={F}, bits={bits}")
+    _same_dtype(scale, ("min", min))
     with torch.cuda.device(data.device):
         out = torch.empty((N, F), dtype=scale.dtype, device=data.device)
-        rc = L.adaqp_unpack_f32(data.data_ptr(), scale.data_ptr(), min.data_ptr(), N, F, bits,
-                                out.data_ptr(), _lib.stream_ptr())
-        _lib.check(rc, "adaqp_unpack_f32")
+        fn = L.adaqp_unpack_f32 if scale.dtype == torch.float32 else L.adaqp_unpack_f16
+        rc = fn(data.data_ptr(), scale.data_ptr(), min.data_ptr(), N, F, bits, out.data_ptr(), _lib.stream_ptr())
+        _lib.check(rc, "adaqp_unpack")
     return out
 
 
 def row_minmax_scale(data: Tensor, bits: int):
-    """Fused compute_minmax_params + scale of integer_quantize (op_util.py:20-22,41)."""
+    """Fused compute_minmax_params + scale of integer_quantize (op_util.py:20-22,41); fp32 only."""
     _check_float_tensor(data, "data", 2)
+    if data.dtype != torch.float32:
+        raise RuntimeError("row_minmax_scale: float32 only")
     L = _lib.load()
     N, F = data.shape
     with torch.cuda.device(data.device):

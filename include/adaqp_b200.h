@@ -76,6 +76,15 @@ int adaqp_pack_f32(const float *data, const float *min, const float *scale,
 int adaqp_unpack_f32(const uint8_t *packed, const float *scale, const float *min,
                      int64_t N, int64_t F, int bits, float *out, void *stream);
 
+/* fp16 instantiation (the reference dispatches AT_DISPATCH_FLOATING_TYPES_AND_HALF, quantization_cuda_kernel.cu:81,138,
+ * and check.h:22-27 admits float16): same layout and generator protocol, c10::Half arithmetic -- every Half (op) Half is
+ * evaluated in float and rounded back to half.  data / min / scale / out are IEEE half arrays.  Not used by the hot
+ * path (boundary messages are fp32); provided for API parity. */
+int adaqp_pack_f16(const void *data, const void *min, const void *scale, int64_t N, int64_t F, int bits,
+                   uint64_t seed, uint64_t offset, uint8_t *packed, void *stream);
+int adaqp_unpack_f16(const uint8_t *packed, const void *scale, const void *min, int64_t N, int64_t F, int bits,
+                     void *out, void *stream);
+
 /* Row min / max / scale = (2^bits-1)/(max-min) in one pass
  * (AdaQP/model/op_util.py:20-22,41).  Any of rmin/rmax/scale may be NULL. */
 int adaqp_row_minmax_f32(const float *data, int64_t N, int64_t F, int bits,

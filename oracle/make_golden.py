@@ -103,6 +103,51 @@ def run_single(qc, name, N, F, bits, kind, dev, seed):
         deq_bf16=deq16.cpu().numpy())
 
 
+HALF_CASES = [
+    # name, N, F, bits, data kind   (fp16 instantiation of the reference kernels)
+    ("h_n7_f13_b2", 7, 13, 2, "normal"),
+    ("h_n8_f100_b4", 8, 100, 4, "normal"),
+    ("h_n5_f602_b8", 5, 602, 8, "normal"),
+    ("h_n33_f256_b2", 33, 256, 2, "relu"),
+    ("h_n16_f256_b4", 16, 256, 4, "relu"),
+    ("h_n3_f300_b8", 3, 300, 8, "grad"),
+    ("h_n9_f200_b1", 9, 200, 1, "normal"),
+    ("h_n6_f64_b4_edge", 6, 64, 4, "edge_half"),
+]
+
+
+def run_single_half(qc, name, N, F, bits, kind, dev, seed):
+    """op_util.py:24-43 with float16 tensors: min / max / scale are computed by torch in half."""
+    rng = np.random.RandomState(seed)
+    if kind == "edge_half":
+        x = rng.standard_normal((N, F)).astype(np.float32)
+        x[0] = 3.25                     # constant row -> scale inf -> NaN -> 0
+        x[1] = 0.0
+        x[2] = 1.0
+        x[2, ::2] = 1.001               # range 0.001 < 15 / 65504: the half scale overflows to inf
+        x[3] = np.where(rng.rand(F) < 0.5, -1.0, 1.0)
+        x[4, 0] = 60000.0
+    else:
+        x = make_data(kind, N, F, rng)
+    xt = torch.from_numpy(x).to(dev).to(torch.float16)
+    rmin = torch.min(xt, dim=1)[0]
+    rmax = torch.max(xt, dim=1)[0]
+    scale = ((2 ** bits - 1) / (rmax - rmin)).to(xt.dtype)
+    torch.cuda.manual_seed(4321 + seed)
+    s0, o0 = gen_state(dev)
+    packed = qc.pack_single_precision(xt, rmin, rmax, scale, bits, True)
+    s1, o1 = gen_state(dev)
+    wpt = 8 // bits
+    payload = ((N + wpt - 1) // wpt) * F
+    deq = qc.unpack_single_precision(packed, bits, scale, rmin, N, F)
+    torch.cuda.synchronize()
+    assert deq.dtype == torch.float16
+    u16 = lambda t: t.view(torch.int16).cpu().numpy().view(np.uint16)
+    return dict(x=u16(xt), bits=np.int32(bits), rmin=u16(rmin), rmax=u16(rmax), scale=u16(scale), seed=np.uint64(s0),
+                offset=np.uint64(o0), offset_after=np.uint64(o1), packed_len=np.int64(packed.numel()),
+                payload=packed[:payload].cpu().numpy().view(np.uint8), deq=u16(deq))
+
+
 def run_mixed(qc, name, S, F, seed, dev):
     """One src->dst channel: mixed_msg_quantization / mixed_msg_dequantization."""
     rng = np.random.RandomState(seed)
@@ -155,11 +200,20 @@ def run_mixed(qc, name, S, F, seed, dev):
                 params=params.view(torch.int16).cpu().numpy().view(np.uint16), deq=out.cpu().numpy())
 
 
-def main(out_dir: str):
+def main(out_dir: str, half_only: bool = False):
     os.makedirs(out_dir, exist_ok=True)
     qc = obuild.load_ref()
     dev = torch.device("cuda:0")
     torch.cuda.set_device(dev)
+    for i, (name, N, F, bits, kind) in enumerate(HALF_CASES):
+        rec = run_single_half(qc, name, N, F, bits, kind, dev, seed=300 + i)
+        np.savez_compressed(os.path.join(out_dir, f"half_{name}.npz"), **rec)
+        print("golden", name, "offset", int(rec["offset"]), "->", int(rec["offset_after"]))
+    if half_only:
+        with open(os.path.join(out_dir, "PROVENANCE_half.txt"), "w") as f:
+            f.write(f"half_*.npz generated by oracle/make_golden.py --half on {torch.cuda.get_device_name(0)} with torch "
+                    f"{torch.__version__}; kernels: reference quant_cuda (fp16 instantiation) built from /root/reference\n")
+        return
     for i, (name, N, F, bits, kind) in enumerate(SINGLE_CASES):
         rec = run_single(qc, name, N, F, bits, kind, dev, seed=100 + i)
         np.savez_compressed(os.path.join(out_dir, f"single_{name}.npz"), **rec)
@@ -175,4 +229,5 @@ def main(out_dir: str):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/golden")
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    main(args[0] if args else "gpurun_out/golden", half_only="--half" in sys.argv)

@@ -51,6 +51,10 @@ def lib():
         L.oracle_pack_at.argtypes = [f32p, f32p, f32p, C.c_int64, C.c_int64, C.c_int,
                                      C.c_uint64, C.c_uint64, C.c_int64, u8p]
         L.oracle_unpack.argtypes = [u8p, f32p, f32p, C.c_int64, C.c_int64, C.c_int, f32p]
+        L.oracle_pack_f16.argtypes = [u16p, u16p, u16p, C.c_int64, C.c_int64, C.c_int, C.c_uint64, C.c_uint64, u8p]
+        L.oracle_unpack_f16.argtypes = [u8p, u16p, u16p, C.c_int64, C.c_int64, C.c_int, u16p]
+        L.oracle_half_to_float_n.argtypes = [u16p, C.c_int64, f32p]
+        L.oracle_float_to_half_n.argtypes = [f32p, C.c_int64, u16p]
         L.oracle_minmax_scale.argtypes = [f32p, C.c_int64, C.c_int64, C.c_int, f32p, f32p, f32p]
         L.oracle_f32_to_bf16_n.argtypes = [f32p, C.c_int64, u16p]
         L.oracle_bf16_to_f32_n.argtypes = [u16p, C.c_int64, f32p]
@@ -140,6 +144,41 @@ def unpack(packed, bits: int, scale, mn, N: int, F: int) -> np.ndarray:
     out = np.zeros((N, F), dtype=np.float32)
     lib().oracle_unpack(_p(packed, C.c_uint8), _p(scale, C.c_float), _p(mn, C.c_float),
                         N, F, bits, _p(out, C.c_float))
+    return out
+
+
+def _u16(a) -> np.ndarray:
+    a = np.asarray(a)
+    if a.dtype == np.float16:
+        a = a.view(np.uint16)
+    return np.ascontiguousarray(a, dtype=np.uint16)
+
+
+def pack_f16(data, mn, scale, bits: int, seed: int, offset: int) -> np.ndarray:
+    """fp16 instantiation of pack_single_precision; inputs are float16 arrays (or their uint16 bits)."""
+    data, mn, scale = _u16(data), _u16(mn), _u16(scale)
+    N, F = data.shape
+    out = np.zeros(packed_nbytes(N, F, bits), dtype=np.uint8)
+    if N:
+        lib().oracle_pack_f16(_p(data, C.c_uint16), _p(mn, C.c_uint16), _p(scale, C.c_uint16), N, F, bits, seed, offset,
+                              _p(out, C.c_uint8))
+    return out
+
+
+def unpack_f16(packed, bits: int, scale, mn, N: int, F: int) -> np.ndarray:
+    packed = np.ascontiguousarray(packed, dtype=np.uint8)
+    scale, mn = _u16(scale), _u16(mn)
+    out = np.zeros((N, F), dtype=np.uint16)
+    if N:
+        lib().oracle_unpack_f16(_p(packed, C.c_uint8), _p(scale, C.c_uint16), _p(mn, C.c_uint16), N, F, bits, _p(out, C.c_uint16))
+    return out.view(np.float16)
+
+
+def half_roundtrip_check(f32: np.ndarray) -> np.ndarray:
+    """float -> half bits with the oracle's own converter (tests compare it with numpy's)."""
+    f32 = _f32(f32).reshape(-1)
+    out = np.zeros(f32.size, np.uint16)
+    lib().oracle_float_to_half_n(_p(f32, C.c_float), f32.size, _p(out, C.c_uint16))
     return out
 
 

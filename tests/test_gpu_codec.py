@@ -167,30 +167,66 @@ def test_side_by_side_with_reference_kernels(qc, N, F, bits):
 
 
 def test_dtype_boundary_matches_reference_checks():
-    """check.h:22-27 admits float32 and float16 and rejects everything else with
-    'The type of <name> is not correct!' (the fp64 kernel instantiation of
-    quantization_cuda_kernel.cu:81 is unreachable behind that check).  This library builds the fp32
-    instantiation only -- the dtype of every boundary message on the hot path (op_util.py:72) -- and
-    refuses float16 explicitly instead of computing in another precision."""
+    """check.h:22-27 admits float32 and float16 and rejects everything else with 'The type of <name> is not correct!'
+    (the fp64 kernel instantiation of quantization_cuda_kernel.cu:81 is unreachable behind that check); mixing dtypes
+    fails like data_ptr<scalar_t>() does; a refused call does not consume the generator."""
     from adaqp_b200 import quant
     dev = torch.device("cuda:0")
     x = torch.randn(8, 32, device=dev)
     mn, mx = x.min(1)[0], x.max(1)[0]
     sc = 15.0 / (mx - mn)
+    gen = torch.cuda.default_generators[0]
+    off = gen.get_offset()
     for bad in (torch.float64, torch.bfloat16, torch.int32):
         with pytest.raises(RuntimeError, match="The type of data is not correct!"):
             quant.pack_single_precision(x.to(bad), mn, mx, sc, 4, True)
     with pytest.raises(RuntimeError, match="The type of scale is not correct!"):
         quant.pack_single_precision(x, mn, mx, sc.double(), 4, True)
-    with pytest.raises(RuntimeError, match="only the float32 instantiation"):
-        quant.pack_single_precision(x.half(), mn.half(), mx.half(), sc.half(), 4, True)
+    with pytest.raises(RuntimeError, match="expected scalar type"):
+        quant.pack_single_precision(x.half(), mn, mx, sc, 4, True)
     q = quant.pack_single_precision(x, mn, mx, sc, 4, True)
-    with pytest.raises(RuntimeError, match="only the float32 instantiation"):
-        quant.unpack_single_precision(q, 4, sc.half(), mn.half(), 8, 32)
+    with pytest.raises(RuntimeError, match="expected scalar type"):
+        quant.unpack_single_precision(q, 4, sc.half(), mn, 8, 32)
     with pytest.raises(RuntimeError, match="The type of scale is not correct!"):
         quant.unpack_single_precision(q, 4, sc.double(), mn, 8, 32)
+    assert gen.get_offset() == off + 64, "only the one successful call consumed the generator (F * 8/bits = 64)"
+
+
+@pytest.mark.parametrize("N,F,bits", [(7, 13, 2), (8, 100, 4), (5, 602, 8), (33, 256, 2), (9, 200, 1), (1, 1, 8)])
+def test_half_codec_vs_oracle_and_reference(qc, N, F, bits):
+    """fp16 instantiation (c10::Half arithmetic): our kernels == the C oracle == the reference's own kernels, bit for bit,
+    including rows whose half scale overflows to inf and constant rows (scale inf -> NaN -> 0)."""
+    from oracle import oracle as O
+    from oracle import build as obuild
+    dev = torch.device("cuda:0")
+    rng = np.random.RandomState(N * 1000 + F + bits)
+    x = rng.standard_normal((N, F)).astype(np.float32)
+    if N > 3:
+        x[0] = 2.5
+        x[1] = 1.0
+        x[1, ::2] = 1.001
+        x[2] *= 1000.0
+    xt = torch.from_numpy(x).to(dev).half()
+    rmin, rmax = torch.min(xt, dim=1)[0], torch.max(xt, dim=1)[0]
+    scale = ((2 ** bits - 1) / (rmax - rmin)).to(torch.float16)
     gen = torch.cuda.default_generators[0]
-    off = gen.get_offset()
-    with pytest.raises(RuntimeError):
-        quant.pack_single_precision(x.half(), mn.half(), mx.half(), sc.half(), 4, True)
-    assert gen.get_offset() == off, "a refused call must not consume the generator"
+    torch.cuda.manual_seed(99)
+    seed, off = gen.initial_seed(), gen.get_offset()
+    packed = qc.pack_single_precision(xt, rmin, rmax, scale, bits, True)
+    assert gen.get_offset() - off == O.philox_offset_increment(F, bits)
+    payload = O.packed_nbytes(N, F, bits)
+    u16 = lambda t: t.view(torch.int16).cpu().numpy().view(np.uint16)
+    want = O.pack_f16(u16(xt), u16(rmin), u16(scale), bits, seed, off)
+    np.testing.assert_array_equal(packed[:payload].cpu().numpy().view(np.uint8), want)
+    deq = qc.unpack_single_precision(packed, bits, scale, rmin, N, F)
+    assert deq.dtype == torch.float16 and deq.shape == (N, F)
+    want_d = O.unpack_f16(want, bits, u16(scale), u16(rmin), N, F)
+    got_d = u16(deq)
+    assert ((got_d == want_d.view(np.uint16)) | (np.isnan(want_d) & np.isnan(got_d.view(np.float16)))).all()
+    if obuild.ref_available():
+        ref = obuild.load_ref()
+        torch.cuda.manual_seed(99)
+        rp = ref.pack_single_precision(xt, rmin, rmax, scale, bits, True)
+        assert torch.equal(rp[:payload], packed[:payload])
+        rd = ref.unpack_single_precision(rp, bits, scale, rmin, N, F)
+        assert ((u16(rd) == got_d) | (torch.isnan(rd) & torch.isnan(deq)).cpu().numpy()).all()

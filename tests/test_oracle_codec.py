@@ -155,3 +155,27 @@ def test_oracle_vs_reference_golden_mixed(path):
     np.testing.assert_array_equal(prm, g["params"])
     deq = O.mixed_dequantize(q, prm, assign, x.shape[1])
     np.testing.assert_array_equal(deq.view(np.uint32), g["deq"].view(np.uint32))
+
+
+def _half_goldens():
+    import glob
+    return sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "half_*.npz")))
+
+
+@pytest.mark.parametrize("path", _half_goldens() or [None])
+def test_half_oracle_vs_reference_golden(path):
+    """fp16 instantiation: the C restatement of c10::Half arithmetic reproduces the reference kernels' packed bytes
+    and dequantised halves bit for bit (goldens recorded on a B200 by oracle/make_golden.py --half)."""
+    if path is None:
+        pytest.skip("no fp16 goldens recorded yet")
+    from oracle import oracle as O
+    g = np.load(path)
+    bits, seed, off = int(g["bits"]), int(g["seed"]), int(g["offset"])
+    N, F = g["x"].shape
+    assert int(g["offset_after"]) - off == O.philox_offset_increment(F, bits)
+    packed = O.pack_f16(g["x"], g["rmin"], g["scale"], bits, seed, off)
+    np.testing.assert_array_equal(packed, g["payload"])
+    deq = O.unpack_f16(g["payload"], bits, g["scale"], g["rmin"], N, F)
+    got, want = deq.view(np.uint16), g["deq"]
+    same = (got == want) | (np.isnan(deq) & np.isnan(want.view(np.float16)))
+    assert same.all()
