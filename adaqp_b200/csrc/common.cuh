@@ -22,6 +22,7 @@ struct AdaqpOptions {
     int spmm_hints;           // bit 0: streaming output stores, bit 1: streaming index loads
     int exch_send_ctas;       // 0 = one resident wave; > 0 = total CTA cap of the send kernels
     int exch_recv_ctas;       // same for the receive kernel
+    int gemm_block_k;         // K block of gemm_tf32x3_kernel: 32 (SWIZZLE_128B, 2 stages) or 16 (SWIZZLE_64B, 4 stages)
 };
 AdaqpOptions &adaqp_options();
 

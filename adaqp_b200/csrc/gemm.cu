@@ -28,14 +28,9 @@ namespace {
 
 constexpr int kGemmThreads = 384;       // 12 warps
 constexpr int kBlockM = 128;
-constexpr int kBlockK = 32;             // fp32 elements = one 128-byte swizzle row
-constexpr int kStages = 2;
+constexpr int kBoxCols = 32;            // fp32 elements of one 128-byte swizzle row (TMA box inner extent, default)
 constexpr int kMaxN = 256;
 constexpr uint32_t kTmemCols = 512;     // two accumulators of up to 256 fp32 columns
-constexpr uint32_t kATile = kBlockM * kBlockK * 4;        // 16 KB
-constexpr uint32_t kBTile = kMaxN * kBlockK * 4;          // 32 KB (N <= 256)
-constexpr uint32_t kStageBytes = 2 * kATile + 2 * kBTile; // A_hi(raw) | A_lo | B_hi | B_lo = 96 KB
-constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*alignment*/ + 256 /*barriers*/;
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -72,17 +67,9 @@ __device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// K-major, SWIZZLE_128B operand tile: rows of 128 bytes, 8-row groups of 1024 bytes (SBO), LBO unused (1),
-// descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B  (cute/arch/mma_sm100_desc.hpp: SmemDescriptor)
-__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);          // start address, 16-byte units
-    d |= (uint64_t)1 << 16;                          // leading byte offset (ignored for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset between 8-row groups
-    d |= (uint64_t)1 << 46;                          // version
-    d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
-    return d;
-}
+// K-major swizzled operand tiles (umma_desc_k below): rows of 128 (64) bytes, 8-row groups SBO = 1024 (512) bytes apart,
+// LBO unused (1), descriptor version 1 (sm_100), layout type SWIZZLE_128B = 2 / SWIZZLE_64B = 4
+// (cute/arch/mma_sm100_desc.hpp: SmemDescriptor).
 // Instruction descriptor (UMMA::InstrDescriptor): D fp32, A/B tf32, K-major both, M = 128, N = n
 __device__ __forceinline__ uint32_t umma_idesc_tf32(int n) {
     uint32_t d = 0;
@@ -102,12 +89,40 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
         "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+// KB = 32: 128-byte rows (SWIZZLE_128B), 96 KB stages, 2 of them; KB = 16: 64-byte rows (SWIZZLE_64B), 48 KB stages,
+// 4 of them -- twice as many TMA -> split -> MMA chains in flight for the same shared memory.
+template <int KB>
+struct GemmCfg {
+    static constexpr int kStages = KB == 32 ? 2 : 4;
+    static constexpr uint32_t kATile = kBlockM * KB * 4;
+    static constexpr uint32_t kBTile = kMaxN * KB * 4;
+    static constexpr uint32_t kStageBytes = 2 * kATile + 2 * kBTile;
+    static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 + 256;
+    static constexpr uint32_t kSbo = 8 * KB * 4;                 // bytes between 8-row groups
+    static constexpr uint64_t kLayout = KB == 32 ? 2 : 4;        // UMMA LayoutType: SWIZZLE_128B / SWIZZLE_64B
+};
+
+template <int KB>
+__device__ __forceinline__ uint64_t umma_desc_k(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(GemmCfg<KB>::kSbo >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= GemmCfg<KB>::kLayout << 61;
+    return d;
+}
+
+template <int KB>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
                    const __grid_constant__ CUtensorMap map_blo, const float *__restrict__ bias,
                    float *__restrict__ C, int64_t ldc, int M, int N, int K) {
+    constexpr int kStages = GemmCfg<KB>::kStages;
+    constexpr int kBlockK = KB;
+    constexpr uint32_t kATile = GemmCfg<KB>::kATile, kBTile = GemmCfg<KB>::kBTile, kStageBytes = GemmCfg<KB>::kStageBytes;
     extern __shared__ uint8_t smem_raw[];
-    const uint32_t base = (smem_addr(smem_raw) + 1023u) & ~1023u;          // SWIZZLE_128B tiles: 1024-byte aligned
+    const uint32_t base = (smem_addr(smem_raw) + 1023u) & ~1023u;          // swizzled tiles: 1024-byte aligned
     uint8_t *gen = smem_raw + (base - smem_addr(smem_raw));
     const uint32_t bars = base + kStages * kStageBytes;
     // barriers: full[s] (TMA landed), split[s] (A_hi / A_lo written), empty[s] (MMAs done with the stage),
@@ -172,10 +187,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     const uint32_t st = base + s * kStageBytes;
 #pragma unroll
                     for (int k = 0; k < kBlockK / 8; ++k) {
-                        const uint64_t ahi = umma_desc_k_sw128(st + k * 32);
-                        const uint64_t alo = umma_desc_k_sw128(st + kATile + k * 32);
-                        const uint64_t bhi = umma_desc_k_sw128(st + 2 * kATile + k * 32);
-                        const uint64_t blo = umma_desc_k_sw128(st + 2 * kATile + kBTile + k * 32);
+                        const uint64_t ahi = umma_desc_k<KB>(st + k * 32);
+                        const uint64_t alo = umma_desc_k<KB>(st + kATile + k * 32);
+                        const uint64_t bhi = umma_desc_k<KB>(st + 2 * kATile + k * 32);
+                        const uint64_t blo = umma_desc_k<KB>(st + 2 * kATile + kBTile + k * 32);
                         umma_tf32(tmem_d, alo, bhi, idesc, (kb | k) != 0);     // small terms first
                         umma_tf32(tmem_d, ahi, blo, idesc, 1);
                         umma_tf32(tmem_d, ahi, bhi, idesc, 1);
@@ -466,13 +481,13 @@ EncodeTiledFn encoder() {
 
 // 2-D fp32 map {cols, rows} (cols contiguous), box {32, box_rows}, SWIZZLE_128B, out-of-bounds elements read as zero
 int make_tile_map(CUtensorMap *m, const float *base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
-                  CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+                  CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B, int box_cols = kBoxCols) {
     // box = {32 columns (one 128-byte swizzle row), box_rows}
     EncodeTiledFn enc = encoder();
     ADAQP_REQUIRE(enc != nullptr, ADAQP_EINVAL, "cuTensorMapEncodeTiled not available from the driver");
     const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-    const cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                            swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -500,18 +515,25 @@ int adaqp_gemm_tf32x3_f32(const float *A, int64_t lda, const float *Bt_hi, const
                   "adaqp_gemm_tf32x3_f32: operands must be 16-byte aligned");
     ADAQP_REQUIRE(M < (1ll << 31), ADAQP_ELIMIT, "adaqp_gemm_tf32x3_f32: M too large");
     const int n_mma = ((N + 15) / 16) * 16;
+    const int kb = adaqp_options().gemm_block_k == 32 ? 32 : 16;
+    const CUtensorMapSwizzle sw = kb == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     CUtensorMap ma, mh, ml;
-    int rc = make_tile_map(&ma, A, M, K, lda, kBlockM);
+    int rc = make_tile_map(&ma, A, M, K, lda, kBlockM, sw, kb);
     if (rc) return rc;
-    rc = make_tile_map(&mh, Bt_hi, N, K, ldb, n_mma);
+    rc = make_tile_map(&mh, Bt_hi, N, K, ldb, n_mma, sw, kb);
     if (rc) return rc;
-    rc = make_tile_map(&ml, Bt_lo, N, K, ldb, n_mma);
+    rc = make_tile_map(&ml, Bt_lo, N, K, ldb, n_mma, sw, kb);
     if (rc) return rc;
     const int sms = adaqp_sm_count() > 0 ? adaqp_sm_count() : 148;
     const int64_t tiles = (M + kBlockM - 1) / kBlockM;
     const int grid = (int)(tiles < sms ? tiles : sms);
-    ADAQP_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    gemm_tf32x3_kernel<<<grid, kGemmThreads, kSmemBytes, (cudaStream_t)stream>>>(ma, mh, ml, bias, C, ldc, (int)M, N, K);
+    if (kb == 32) {
+        ADAQP_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmCfg<32>::kSmemBytes));
+        gemm_tf32x3_kernel<32><<<grid, kGemmThreads, GemmCfg<32>::kSmemBytes, (cudaStream_t)stream>>>(ma, mh, ml, bias, C, ldc, (int)M, N, K);
+    } else {
+        ADAQP_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmCfg<16>::kSmemBytes));
+        gemm_tf32x3_kernel<16><<<grid, kGemmThreads, GemmCfg<16>::kSmemBytes, (cudaStream_t)stream>>>(ma, mh, ml, bias, C, ldc, (int)M, N, K);
+    }
     return adaqp_check_launch("gemm_tf32x3_kernel");
 }
 

@@ -47,6 +47,7 @@ int adaqp_sm_count(void);
  * variables onto these once at load).  Names: "spmm_impl" (1 register gather [default], 2 cp.async
  * ring, 3 TMA tile::gather4 ring, 4 TMA bulk-per-row ring), "spmm_rows_per_grab" (0 = default),
  * "spmm_ctas_per_sm", "spmm_hints" (bit 0 streaming output stores, bit 1 streaming index loads),
+ * "gemm_block_k" (32 or 16: K block / swizzle width of the dense GEMM),
  * "exch_send_ctas" / "exch_recv_ctas" (0 = one resident wave over all SMs, n = at most n CTAs, so
  * that the exchange kernels leave the remaining SMs to the overlapped aggregation,
  * SURVEY.md 7 step 7 -- the reference instead serialises them, ops.py:119-130). */

@@ -19,9 +19,20 @@ def dense():
     return d
 
 
+@pytest.mark.parametrize("kb", [32, 16], ids=["K32-sw128-2stages", "K16-sw64-4stages"])
 @pytest.mark.parametrize("M,K,N", [(128, 32, 16), (1000, 256, 256), (4099, 100, 256), (333, 256, 47), (257, 200, 256),
                                    (70001, 256, 256), (5, 8, 8), (129, 300, 100)])
-def test_matches_float64(dense, M, K, N):
+def test_matches_float64(dense, M, K, N, kb):
+    from adaqp_b200 import _lib
+    old = _lib.get_option("gemm_block_k")
+    _lib.set_option("gemm_block_k", kb)
+    try:
+        _matches_float64(dense, M, K, N)
+    finally:
+        _lib.set_option("gemm_block_k", old)
+
+
+def _matches_float64(dense, M, K, N):
     torch.manual_seed(M + K + N)
     dev = torch.device("cuda:0")
     x = torch.randn(M, K, device=dev)

@@ -18,7 +18,14 @@ def main():
             b = torch.randn(N, device=dev)
             wt = w.t().contiguous()
             res = {"M": M, "K": K, "N": N}
-            for name, fn in (("tcgen05_3xtf32", lambda: dense.gemm_nt(x, w, b)), ("torch_fp32", lambda: torch.addmm(b, x, wt))):
+            from adaqp_b200 import _lib
+
+            def with_kb(kb):
+                def run():
+                    _lib.set_option("gemm_block_k", kb)
+                    return dense.gemm_nt(x, w, b)
+                return run
+            for name, fn in (("tcgen05_3xtf32", with_kb(32)), ("tcgen05_3xtf32_k16", with_kb(16)), ("torch_fp32", lambda: torch.addmm(b, x, wt))):
                 for _ in range(3):
                     fn()
                 ts = []
