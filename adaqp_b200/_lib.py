@@ -88,6 +88,10 @@ SYMBOLS = {
     "adaqp_wgrad_tf32x3_supported": (C.c_int, [i64, i32, i32, i64, i64]),
     "adaqp_wgrad_tf32x3_grid": (C.c_int, [i64]),
     "adaqp_wgrad_tf32x3_f32": (C.c_int, [c_void_p, i64, c_void_p, i64, i64, i32, i32, c_void_p, i32, c_void_p]),
+    "adaqp_ln_relu_grid": (C.c_int, [i64]),
+    "adaqp_ln_relu_fwd_f32": (C.c_int, [c_void_p, i64, c_void_p, c_void_p, C.c_float, i64, i32, c_void_p, i64, c_void_p, c_void_p, c_void_p]),
+    "adaqp_ln_relu_bwd_f32": (C.c_int, [c_void_p, i64, c_void_p, i64, c_void_p, c_void_p, c_void_p, c_void_p, i64, i32, c_void_p, i64,
+                                        c_void_p, i32, c_void_p]),
     "adaqp_gather_rows_f32": (C.c_int, [c_void_p, i64, c_void_p, i64, i32, c_void_p, i64,
                                         c_void_p]),
 }

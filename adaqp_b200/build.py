@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_build")
 LIB = os.path.join(HERE, "libadaqp_b200.so")
-SOURCES = ["runtime.cu", "quant.cu", "exchange.cu", "spmm.cu", "gemm.cu"]
+SOURCES = ["runtime.cu", "quant.cu", "exchange.cu", "spmm.cu", "gemm.cu", "norm.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"),
            os.path.join(os.path.dirname(HERE), "include", "adaqp_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -13,7 +13,7 @@ from torch import Tensor
 from torch.nn import init
 from torch.nn.parameter import Parameter
 
-from .. import dense
+from .. import dense, fused
 from .ops import DistAggConv
 
 
@@ -60,6 +60,7 @@ class DistGCN(nn.Module):
             feats = self.convs[i](feats, g, i)
             feats = F.dropout(feats, p=self.drop_rate, training=self.training)
             if hasattr(self, "norms"):
-                feats = self.norms[i](feats)
-            feats = F.relu(feats, inplace=True)
+                feats = fused.layer_norm_relu(feats, self.norms[i])      # relu(norms[i](feats)), one pass (csrc/norm.cu)
+            else:
+                feats = F.relu(feats, inplace=True)
         return self.convs[last](feats, g, last)

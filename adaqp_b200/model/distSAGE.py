@@ -11,7 +11,7 @@ from torch import Tensor
 from torch.nn import init
 from torch.nn.parameter import Parameter
 
-from .. import dense
+from .. import dense, fused
 from .ops import DistAggSAGE
 
 
@@ -67,6 +67,7 @@ class DistSAGE(nn.Module):
             feats = self.sages[i](feats, g, i)
             feats = F.dropout(feats, p=self.drop_rate, training=self.training)
             if hasattr(self, "norms"):
-                feats = self.norms[i](feats)
-            feats = F.relu(feats)
+                feats = fused.layer_norm_relu(feats, self.norms[i])      # relu(norms[i](feats)), one pass (csrc/norm.cu)
+            else:
+                feats = F.relu(feats)
         return self.sages[last](feats, g, last)

@@ -298,10 +298,10 @@ def run_ours(args, rank, world):
     p2p = comm.ctx.comm_buffer.p2p
     if p2p is not None:
         p2p.profile = True
-    from adaqp_b200 import dense
-    gemm_before = dict(dense.LAUNCHES)
+    from adaqp_b200 import dense, fused
+    gemm_before = {**dense.LAUNCHES, **fused.LAUNCHES}
     ms, traced_all = timed(args.steps, dev_step)
-    gemm_launches = {k: dense.LAUNCHES[k] - gemm_before[k] for k in dense.LAUNCHES}
+    gemm_launches = {k: {**dense.LAUNCHES, **fused.LAUNCHES}[k] - gemm_before[k] for k in gemm_before}
     exch_times = None
     if p2p is not None:
         exch_times = p2p.kernel_times_ms()
@@ -383,7 +383,8 @@ def run_ours(args, rank, world):
                      "gather_bound": {"note": "no-reuse bound 4*F*nnz: what a random gather must move when the source matrix exceeds L2",
                                       "achieved_GBps": sum(4 * F * int(eng.layout.indptr[-1]) for F in [dims[0], dims[1], dims[2], dims[2], dims[1]]) / (agg_ms * 1e-3) / 1e9}},
         "dense_gemm": {"kernels_per_epoch": {k: v // max(args.steps, 1) for k, v in gemm_launches.items()},
-                       "arithmetic": "tcgen05 kind::tf32 x3 (error-compensated split, fp32 accumulate)" if dense.enabled() else "torch.matmul fp32"},
+                       "arithmetic": "tcgen05 kind::tf32 x3 (error-compensated split, fp32 accumulate)" if dense.enabled() else "torch.matmul fp32",
+                       "layer_norm_relu": "fused (csrc/norm.cu)" if fused.enabled() else "torch"},
         "final_loss": losses[-1],
         "exchange": exchange_stats(comm.ctx.comm_buffer.p2p, eng, traced_all) if world > 1 else None,
         "roofline_exchange": exchange_roofline(comm.ctx.comm_buffer.p2p, eng, exch_times, args.steps, peaks["hbm_gbs"]) if world > 1 else None,

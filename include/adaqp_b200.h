@@ -254,6 +254,18 @@ int adaqp_wgrad_tf32x3_grid(int64_t M);
 int adaqp_wgrad_tf32x3_f32(const float *dY, int64_t ldy, const float *X, int64_t ldx, int64_t M, int32_t N, int32_t K,
                            float *partials, int32_t grid, void *stream);
 
+/* ------------------------------------------------------ LayerNorm + ReLU
+ * y = relu(LayerNorm(x) * gamma + beta) over the last dimension (biased variance, eps as nn.LayerNorm), forward and
+ * backward in one pass each: the `self.norms[i](feats)` + `F.relu` between aggregations (AdaQP/model/distGCN.py:81-84,
+ * distSAGE.py:93-96).  F % 4 == 0, F <= 1024, 16-byte aligned rows.  The backward writes per-CTA partial column sums
+ * partials[grid][2][F] (dgamma, dbeta; grid = adaqp_ln_relu_grid(M)) that the caller adds.  Dropout stays torch's. */
+int adaqp_ln_relu_grid(int64_t M);
+int adaqp_ln_relu_fwd_f32(const float *x, int64_t ldx, const float *gamma, const float *beta, float eps, int64_t M,
+                          int32_t F, float *y, int64_t ldy, float *mean, float *rstd, void *stream);
+int adaqp_ln_relu_bwd_f32(const float *dy, int64_t lddy, const float *x, int64_t ldx, const float *mean,
+                          const float *rstd, const float *gamma, const float *beta, int64_t M, int32_t F, float *dx,
+                          int64_t lddx, float *partials, int32_t grid, void *stream);
+
 /* Row gather out[i] = x[idx[i]] (copy-buffer fills of ops.py:159-164; API parity only). */
 int adaqp_gather_rows_f32(const float *x, int64_t ld, const int64_t *idx, int64_t n,
                           int32_t F, float *out, int64_t ldo, void *stream);
