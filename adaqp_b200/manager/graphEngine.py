@@ -156,6 +156,13 @@ class GraphEngine(object):
         L = layout if layout is not None else load_rank_layout(part_dir, dataset, model_type)
         self.layout = L
         self._is_bidirected = L.is_bidirected
+        if not L.is_bidirected:
+            # The reference builds bwd_graph = dgl.reverse(graph, copy_ndata=False) (graphEngine.py:135-147): the reversed
+            # graph carries no 'in_degrees' / 'out_degrees', which its backward aggregation reads (ops.py:23-24,50), and the
+            # reverse of the LOCAL graph has no edge back to the owners of halo sources, so their gradient share would be
+            # dropped.  Its four datasets are symmetrised (helper/partition.py:58-60); directed input is refused up front.
+            raise NotImplementedError("directed (non-symmetrised) partitions are not supported: in_degrees != out_degrees; "
+                                      "symmetrise the graph before partitioning as the reference's helper/partition.py does")
         self._use_parallel = use_parallel
         if msg_precision_type == "full":
             self._bit_type = BitType.FULL
@@ -181,9 +188,6 @@ class GraphEngine(object):
         else:
             from .graph_cpu import CpuGraph          # gloo plumbing mode only
             self.local_graph = CpuGraph(L.indptr, L.indices, L.in_degrees, L.out_degrees, L.n_inner, L.n_halo)
-        if not L.is_bidirected:
-            raise NotImplementedError("directed partitions need a reversed CSR for the backward pass; "
-                                      "all four reference datasets are symmetrised (partition.py:58-60)")
         if use_parallel:
             self.graph = DecompGraph(RowRange(self.local_graph, 0, L.n_central),
                                      RowRange(self.local_graph, L.n_central, L.n_inner),

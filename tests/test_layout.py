@@ -75,3 +75,24 @@ def test_rank_layout_contract(model):
         # reorder preserved the multiset of (feature row, degree)
         assert np.isclose(L.feat.sum(), raw.feat.sum(), rtol=1e-4)
         np.testing.assert_array_equal(np.sort(L.in_degrees[:L.n_inner]), np.sort(raw.in_degrees[:raw.n_inner]))
+
+
+def test_directed_partition_is_detected_and_refused():
+    """is_bidirected follows conversion.py:28-32 (all(in_degrees == out_degrees)); a directed layout is refused before any
+    device work (the reference's reversed backward graph cannot run either)."""
+    from adaqp_b200.manager import GraphEngine
+    from adaqp_b200.manager import layout as lay
+    from adaqp_b200.manager.partition_synth import attach_global_degrees
+    from adaqp_b200.manager import conversion as cv
+    spec = small_spec(W=1, n=300)
+    L = prepare_all_in_process(spec)[0]
+    assert L.is_bidirected
+    raws = build_all_partitions(spec)
+    raws[0].out_degrees = raws[0].out_degrees.copy()
+    raws[0].out_degrees[0] += 1                                   # one node with out-degree != in-degree
+    recv_idx, requests = cv.halo_requests(raws[0], DistGNNType.DistGCN)
+    send_ids, scores = cv.send_side(0, [requests])
+    Ld = lay._finish(raws[0], recv_idx, send_ids, scores)
+    assert not Ld.is_bidirected
+    with pytest.raises(NotImplementedError, match="directed"):
+        GraphEngine(1, None, "t", "full", DistGNNType.DistGCN, layout=Ld)
