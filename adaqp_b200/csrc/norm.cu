@@ -101,15 +101,34 @@ ln_relu_bwd_kernel(const float *__restrict__ dy, int64_t lddy, const float *__re
         for (int e = 0; e < 4; ++e) { acc_g[c][e] = 0.f; acc_b[c][e] = 0.f; }
     }
     const float inv_f = 1.0f / (float)F;
+    // software pipeline: the loads of this warp's NEXT row are issued before the current row's reductions, so that two rows
+    // per warp are in flight (at 2 resident CTAs x 8 warps per SM one row per warp leaves HBM half idle: 3.5 TB/s under ncu)
+    float4 nx[CHUNKS], nd[CHUNKS];
+    float nmu = 0.f, nrs = 0.f;
+    auto fetch = [&](int64_t r) {
+        nmu = __ldg(mean + r);
+        nrs = __ldg(rstd + r);
+#pragma unroll
+        for (int c = 0; c < CHUNKS; ++c)
+            if (ok[c]) {
+                nx[c] = ldg_stream_f4(x + r * ldx + (c * 32 + lane) * 4);
+                nd[c] = ldg_stream_f4(dy + r * lddy + (c * 32 + lane) * 4);
+            }
+    };
+    if (warp < M) fetch(warp);
     for (int64_t row = warp; row < M; row += nwarps) {
-        const float mu = __ldg(mean + row), rs = __ldg(rstd + row);
+        const float mu = nmu, rs = nrs;
+        float4 cx[CHUNKS], cd[CHUNKS];
+#pragma unroll
+        for (int c = 0; c < CHUNKS; ++c) { cx[c] = nx[c]; cd[c] = nd[c]; }
+        if (row + nwarps < M) fetch(row + nwarps);
         float xh[CHUNKS][4], gg[CHUNKS][4];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int c = 0; c < CHUNKS; ++c) {
             if (ok[c]) {
-                const float4 xv = ldg_stream_f4(x + row * ldx + (c * 32 + lane) * 4);
-                const float4 dv = ldg_stream_f4(dy + row * lddy + (c * 32 + lane) * 4);
+                const float4 xv = cx[c];
+                const float4 dv = cd[c];
                 const float xe[4] = {xv.x, xv.y, xv.z, xv.w}, de[4] = {dv.x, dv.y, dv.z, dv.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {

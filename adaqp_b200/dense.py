@@ -10,8 +10,9 @@ Backward: dX = dY @ W^T runs through the same kernel; dW = dY^T @ X (reduction o
 dimension) through the split-K kernel `adaqp_wgrad_tf32x3_f32`, which reads both operands
 MN-major straight from their row-major storage; the bias gradient stays a torch reduction.
 
-Shapes the kernel does not take (row pitch not a multiple of 16 bytes, N > 256, CPU tensors) and
-`ADAQP_GEMM=0` use torch.matmul, the reference's own arithmetic.
+Shapes the kernel does not take (input row pitch not a multiple of 16 bytes such as F = 602, N > 256, CPU tensors) and
+`ADAQP_GEMM=0` use torch.matmul, the reference's own arithmetic; the 47-wide gradient of the last layer is zero-padded
+to 48 columns once and runs through the kernels.
 """
 from __future__ import annotations
 
@@ -62,7 +63,7 @@ def gemm_nt(x: Tensor, bt: Tensor, bias: Tensor = None) -> Tensor:
     """x [M, K] @ bt[N, K]^T (+ bias) through the C ABI (no autograd)."""
     M, K = x.shape
     N = bt.shape[0]
-    assert bt.shape[1] == K
+    assert bt.shape[1] == K or (bt.shape[1] + 3) // 4 * 4 == K      # x may carry the zero-padded K already
     bt = _pad_cols(bt)
     hi, lo = split_tf32(bt)
     out = torch.empty((M, N), dtype=torch.float32, device=x.device)
@@ -112,12 +113,16 @@ class _LinearNK(Function):
         x, w_nk = ctx.saved_tensors
         dy = dy.contiguous()
         dx = dw = db = None
+        N = dy.shape[1]
+        # a gradient whose row pitch is not a multiple of 16 bytes (the 47-class last layer) is zero-padded once so that
+        # TMA can address it; the padded columns meet zero weights / are sliced off the result
+        dyp = torch.nn.functional.pad(dy, (0, -N % 4)) if N % 4 and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]) else dy
         if ctx.needs_input_grad[0]:
             # dX[M, K] = dY[M, N] @ W_nk[N, K] = dY @ (W_nk^T)[K, N]^T
             wt = w_nk.t().contiguous()
-            dx = gemm_nt(dy, wt) if supported(dy, wt.shape[0], wt.shape[1]) else dy @ w_nk
+            dx = gemm_nt(dyp, wt) if supported(dyp, wt.shape[0], dyp.shape[1]) else dy @ w_nk
         if ctx.needs_input_grad[1]:
-            dw = gemm_tn(dy, x) if wgrad_supported(dy, x) else dy.t() @ x
+            dw = gemm_tn(dyp, x)[:N] if wgrad_supported(dyp, x) else dy.t() @ x
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy.sum(0)
         return dx, dw, db

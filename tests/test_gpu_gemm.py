@@ -62,6 +62,18 @@ def test_autograd_and_fallbacks(dense):
     (x2 @ w2 + b2).square().sum().backward()
     for g, g2 in ((x.grad, x2.grad), (w.grad, w2.grad), (b.grad, b2.grad)):
         assert ((g.double() - g2).abs().max() / g2.abs().max()).item() < 1e-5
+    # the 47-class last layer: forward on the kernel, its 47-wide gradient zero-padded to 48 columns for dX and dW
+    before = dict(dense.LAUNCHES)
+    w47 = (torch.randn(256, 47, device=dev) * 0.1).requires_grad_()
+    b47 = torch.zeros(47, device=dev, requires_grad=True)
+    xl = x.detach().clone().requires_grad_()
+    torch.log_softmax(dense.linear(xl, w47, b47), 1)[:, 3].sum().backward()
+    x4, w4, b4 = (t.detach().double().requires_grad_() for t in (xl, w47, b47))
+    torch.log_softmax(x4 @ w4 + b4, 1)[:, 3].sum().backward()
+    for g, g2 in ((xl.grad, x4.grad), (w47.grad, w4.grad), (b47.grad, b4.grad)):
+        assert g.shape == g2.shape and ((g.double() - g2).abs().max() / g2.abs().max()).item() < 1e-5
+    assert dense.LAUNCHES["gemm_tf32x3_kernel"] == before["gemm_tf32x3_kernel"] + 2
+    assert dense.LAUNCHES["wgrad_tf32x3_kernel"] == before["wgrad_tf32x3_kernel"] + 1
     # nn.Linear storage
     lin = torch.nn.Linear(256, 64, bias=False).to(dev)
     y = dense.linear_nk(x.detach(), lin.weight)
@@ -74,7 +86,7 @@ def test_autograd_and_fallbacks(dense):
 
 
 @pytest.mark.parametrize("M,N,K", [(16, 128, 32), (1000, 256, 256), (4099, 256, 100), (70001, 256, 256), (333, 128, 200),
-                                   (50, 64, 256), (7, 256, 8), (3000, 100, 256)])
+                                   (50, 64, 256), (7, 256, 8), (3000, 100, 256), (3001, 48, 256)])
 def test_weight_gradient_split_k(dense, M, N, K):
     """dW = dY^T X on the tensor cores (MN-major operands, split over the rows) vs float64."""
     torch.manual_seed(M + N + K)
