@@ -15,7 +15,6 @@ import time
 from itertools import chain
 from typing import Dict, List, Tuple, Union
 
-import numpy as np
 import torch
 from torch import Tensor
 

@@ -17,7 +17,7 @@ the rank alpha * (MB of all its channels) + beta (assigner/solver.py).
 from __future__ import annotations
 
 import time
-from typing import Dict, List, Tuple
+from typing import Dict, Tuple
 
 import numpy as np
 import torch

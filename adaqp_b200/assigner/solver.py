@@ -35,7 +35,7 @@ of one layer cost the same bytes per bit-width in every channel.
 from __future__ import annotations
 
 import itertools
-from typing import Dict, List, Tuple
+from typing import Dict, List
 
 import numpy as np
 

@@ -21,8 +21,8 @@ cross edge agree.
 from __future__ import annotations
 
 import os
-from dataclasses import dataclass, field, asdict
-from typing import Dict, List, Optional, Tuple
+from dataclasses import dataclass, asdict
+from typing import List, Optional, Tuple
 
 import numpy as np
 import scipy.sparse as sp

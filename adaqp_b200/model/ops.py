@@ -11,7 +11,7 @@ aggregate on the default stream; ordering is by CUDA events only.
 """
 from __future__ import annotations
 
-from typing import Any, Tuple, Union
+from typing import Any, Tuple
 
 import torch
 from torch import Tensor

@@ -20,8 +20,7 @@ recorded on a B200 under tests/golden/ + Philox known-answer vectors).
 from __future__ import annotations
 
 import ctypes as C
-import os
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Sequence, Tuple
 
 import numpy as np
 

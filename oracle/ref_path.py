@@ -19,13 +19,12 @@ all-reduce is the reference's per-parameter gloo all_reduce on CUDA tensors (:71
 """
 from __future__ import annotations
 
-import json
 import os
 import time
 from multiprocessing import Event
 from multiprocessing.pool import ThreadPool
 from queue import Queue
-from typing import Dict, List, Tuple
+from typing import Dict
 
 import numpy as np
 import torch

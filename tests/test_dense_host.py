@@ -1,6 +1,5 @@
 """Host side of the tcgen05 dense path (adaqp_b200/dense.py) that needs no GPU: the tf32 operand split is exact,
 and on CPU tensors / unsupported shapes `linear` is torch.matmul (the reference's arithmetic, distGCN.py:45)."""
-import numpy as np
 import torch
 
 from adaqp_b200 import dense

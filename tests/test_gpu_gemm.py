@@ -4,7 +4,6 @@ Tolerance: per product the split drops a_lo*b_lo (<= 2^-22 |ab|) and truncates t
 (<= 2^-22 |ab| each), so |err| <= ~1e-6 * sum|a||b| per output; asserted at 2e-6 relative to the
 row-wise L1 mass (torch's own fp32 SIMT GEMM measures ~1e-7 on the same inputs; a plain 1xTF32 GEMM
 ~5e-4, which the test also checks we are far below)."""
-import numpy as np
 import pytest
 import torch
 

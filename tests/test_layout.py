@@ -82,7 +82,6 @@ def test_directed_partition_is_detected_and_refused():
     device work (the reference's reversed backward graph cannot run either)."""
     from adaqp_b200.manager import GraphEngine
     from adaqp_b200.manager import layout as lay
-    from adaqp_b200.manager.partition_synth import attach_global_degrees
     from adaqp_b200.manager import conversion as cv
     spec = small_spec(W=1, n=300)
     L = prepare_all_in_process(spec)[0]

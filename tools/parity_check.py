@@ -210,7 +210,6 @@ def current_assignment() -> Dict[str, Dict[int, torch.Tensor]]:
 
 
 def activation_parity(trainer, seed: int = 1234, overlapped: bool = False) -> Dict:
-    import torch.distributed as dist
     from oracle import build as obuild
     from oracle import ref_path
     from adaqp_b200.communicator import Communicator as comm
