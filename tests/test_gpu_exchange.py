@@ -183,3 +183,26 @@ def test_fused_equals_single_codec_calls(env):
     assert gen.get_offset() - off == e.quant_plans[key].philox_increment
     for e in exs:
         e.close()
+
+
+def test_dead_peer_times_out_and_raises(env):
+    """A peer that never sends / never acks: the bounded spins give up after timeout_ns, set the status word, and
+    check_status() -- which train_for_one_epoch and val_test poll -- raises instead of letting stale halos through."""
+    spec, lays, exs, dev = make_world(env, 2, 600, 8, [32, 32, 32])
+    for e in exs:
+        e.timeout_ns = 50_000_000                         # 50 ms
+    x0 = torch.randn(lays[0].n_inner, 32, device=dev)
+    exs[0].post_send_fp("test0", x0)                      # rank 1 never posts its send
+    exs[0].complete_recv_fp("test0")
+    torch.cuda.synchronize()
+    with pytest.raises(RuntimeError, match="flag wait timed out"):
+        exs[0].check_status()
+    exs[1].check_status()                                 # the silent rank has nothing to report
+    exs[0].status.zero_()
+    exs[0].post_send_fp("test1", x0)
+    exs[0].post_send_fp("test1", x0)                      # rank 1 never consumed the first payload: no ack
+    torch.cuda.synchronize()
+    with pytest.raises(RuntimeError, match="ack wait timed out"):
+        exs[0].check_status()
+    for e in exs:
+        e.close()
