@@ -17,6 +17,7 @@ import logging
 import json
 import os
 from multiprocessing import Event
+from multiprocessing.pool import ThreadPool
 from typing import List, Tuple
 
 import numpy as np
@@ -217,6 +218,9 @@ class GraphEngine(object):
             self.marginal_stream = self.quant_cuda_event = self.comp_cuda_event = None
         self.quant_cpu_event = Event()
         self.comp_cpu_event = Event()
+        # helper thread of the reference (graphEngine.py:131); only the gloo plumbing transport uses it -- on p2p the
+        # exchange is a kernel on marginal_stream and needs no thread
+        self.marginal_pool = ThreadPool(processes=1) if self._device.type != "cuda" else None
         self.marginal_pool = None
 
     # ---- read-only accessors of the reference (graphEngine.py:169-224), generated below ------------------

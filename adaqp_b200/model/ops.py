@@ -201,11 +201,15 @@ def decomposed_graph_propagation(ctx, local_messages: Tensor, graph, layer: int,
     local_messages = local_messages.contiguous()
     eng, timer = engine.ctx, engine.ctx.timer
     if comm.ctx.transport != "p2p":
-        # gloo transport: no helper thread here; the exchange is synchronous (documented)
-        remote = msg_all2all_GLOO(local_messages[eng.total_send_idx], name, is_train)
+        # gloo plumbing transport: the exchange runs in the helper thread while this thread aggregates the central
+        # rows, as in the reference (ops.py:164-177: marginal_pool.apply_async ... response.get())
+        send_messages = local_messages[eng.total_send_idx]
+        pool = getattr(eng, "marginal_pool", None)
+        response = pool.apply_async(msg_all2all_GLOO, (send_messages, name, is_train)) if pool is not None else None
         out = local_messages.new_empty((eng.num_inner, local_messages.shape[1]))
         with timer.record(f"{name}_central_aggregation"):
             _aggregate(class_name, graph.central_graph, local_messages, None, mode, out[:eng.num_central])
+        remote = response.get() if response is not None else msg_all2all_GLOO(send_messages, name, is_train)
         with timer.record(f"{name}_marginal_aggregation"):
             _aggregate(class_name, graph.marginal_graph, local_messages, remote, mode, out[eng.num_central:])
         return _finish(ctx, out, layer, mode)

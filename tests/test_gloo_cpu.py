@@ -51,6 +51,13 @@ def _worker(rank, world, port, tmp, mode, model_name, out, dataset="reddit"):
         eng.timer.clear(is_train=False)
         b = tr.model(eng.graph, eng.feats)
     assert torch.equal(a, b)
+    if getattr(eng, "marginal_pool", None) is not None:      # overlap modes: helper-thread exchange == synchronous exchange
+        pool, eng.marginal_pool = eng.marginal_pool, None
+        with torch.no_grad():
+            eng.timer.clear(is_train=False)
+            c = tr.model(eng.graph, eng.feats)
+        eng.marginal_pool = pool
+        assert torch.equal(a, c)
     assert not any(k.startswith("forward0") for k in list(eng.timer._record) + list(eng.timer._events))
     assert any(k.startswith("forward1") for k in list(eng.timer._record) + list(eng.timer._events))
     eng.timer.clear(is_train=False)
