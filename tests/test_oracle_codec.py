@@ -179,3 +179,24 @@ def test_half_oracle_vs_reference_golden(path):
     got, want = deq.view(np.uint16), g["deq"]
     same = (got == want) | (np.isnan(deq) & np.isnan(want.view(np.float16)))
     assert same.all()
+
+
+@pytest.mark.parametrize("bits", [2, 4, 8])
+@pytest.mark.parametrize("N,F", [(37, 13), (64, 100), (5, 256)])
+def test_pack_at_windows_equal_slices_of_the_full_call(bits, N, F):
+    """oracle_pack_at restates any window of byte-rows of a pack call with the Philox subsequences that window has in the
+    full call -- the property tools/parity_check.py relies on to check full-scale exchanges window by window."""
+    rng = np.random.RandomState(bits * 1000 + N + F)
+    x = rng.standard_normal((N, F)).astype(np.float32)
+    x[3] = 2.5                                               # constant row: scale = inf
+    mn, _, scale = O.minmax_scale(x, bits)
+    seed, off = 77, 12
+    full = O.pack(x, mn, scale, bits, seed, off)
+    wpt = 8 // bits
+    groups = (N + wpt - 1) // wpt
+    for g0, g1 in [(0, 1), (0, groups), (groups - 1, groups), (1, max(2, groups // 2)), (groups // 2, groups)]:
+        g1 = min(max(g1, g0 + 1), groups)
+        r0, r1 = g0 * wpt, min(g1 * wpt, N)
+        got = O.pack_at(x[r0:r1], mn[r0:r1], scale[r0:r1], bits, seed, off, g0)
+        assert np.array_equal(got, full[g0 * F:g1 * F]), (g0, g1)
+    assert O.pack_at(x[:0], mn[:0], scale[:0], bits, seed, off, 0).size == 0
