@@ -154,6 +154,17 @@ def exchange_stats(ex, eng, traced_all):
             "exchange_region_ms_per_epoch": exch_ms}
 
 
+def dram_rate(traffic_per_launch, launches, agg_ms, hbm_peak):
+    """Measured DRAM rate of the aggregation launches: ncu dram bytes per launch (profiles/spmm_traffic.json) x the
+    launches of an epoch / their event-timed duration, next to the copy peak.  None where no capture exists."""
+    if not traffic_per_launch or not agg_ms or not launches:
+        return None
+    gbps = float(traffic_per_launch) * int(launches) / (float(agg_ms) * 1e-3) / 1e9
+    return {"GBps": gbps, "frac_of_peak": gbps / float(hbm_peak),
+            "note": "ncu DRAM bytes (read + write) of the epoch's aggregation launches / their event-timed duration: what the kernel "
+                    "actually moves, mostly L2 misses this graph makes unavoidable (profiles/r02_spmm.md)"}
+
+
 def exchange_roofline(ex, eng, times, epochs, hbm_peak):
     """Second roofline block: the send and receive kernels of the exchange, each timed ALONE with CUDA
     events on the stream it runs on (rank 0, sums over the timed epochs), against both bounds.
@@ -380,6 +391,7 @@ def run_ours(args, rank, world):
         "roofline": {"kernel": "spmm_csr_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
                      "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_per_shape": traffic_detail, "peak_kind": f"of {peak_kind}",
                      "algorithmic_bytes_per_epoch": alg_bytes, "launches_per_epoch": launches, "spmm_ms_per_epoch": agg_ms,
+                     "dram_rate": dram_rate(traffic, launches, agg_ms, peaks["hbm_gbs"]),
                      "gather_bound": {"note": "no-reuse bound 4*F*nnz: what a random gather must move when the source matrix exceeds L2",
                                       "achieved_GBps": sum(4 * F * int(eng.layout.indptr[-1]) for F in [dims[0], dims[1], dims[2], dims[2], dims[1]]) / (agg_ms * 1e-3) / 1e9}},
         "dense_gemm": {"kernels_per_epoch": {k: v // max(args.steps, 1) for k, v in gemm_launches.items()},

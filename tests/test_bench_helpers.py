@@ -37,3 +37,10 @@ def test_clock_summary_and_peaks():
     assert out["sm_max_mhz"] == 1965 and out["reasons"] == ["sw_power_cap"] and out["sm_mhz"] in (1900, 1965)
     peaks, kind = bench.measured_peaks()
     assert peaks["hbm_gbs"] > 1000 and kind in ("measured", "fallback")
+
+
+def test_dram_rate_block():
+    import bench
+    r = bench.dram_rate(54702720400.0, 5, 56.1, 6480.5)
+    assert abs(r["GBps"] - 4875.5) < 1.0 and abs(r["frac_of_peak"] - 0.7523) < 1e-3
+    assert bench.dram_rate(None, 5, 56.1, 6480.5) is None and bench.dram_rate(1e9, 0, 1.0, 6480.5) is None
